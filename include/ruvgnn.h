@@ -1,0 +1,190 @@
+/*
+ * ruvgnn.h -- C ABI of libruvgnn.so: the B200 (sm_100a) backend for
+ * ruvector-gnn's RuvectorLayer forward over an HNSW neighbourhood graph.
+ *
+ * This is the boundary a `cuda` sub-module of ruvector_gnn::layer would bind
+ * (INTEGRATION.md shows the Rust `extern "C"` block).  Plain pointers and
+ * sizes only; no C++/torch types.  All reference citations are relative to
+ * /root/reference/ (Mu-L/ruvector 2.0.5).
+ *
+ * Conventions (pattern of crates/ruvector-fpga-transformer/src/ffi/c_abi.rs:20-76):
+ *   - every call returns an int32 status, 0 = OK; never panics/aborts;
+ *   - opaque handles are created and destroyed by paired functions;
+ *   - the library copies what it needs and never frees caller memory;
+ *   - output buffers are caller-allocated;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     returns RUVGNN_ERR_CUDA.
+ */
+#ifndef RUVGNN_H
+#define RUVGNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..7 mirror GnnError's variants (crates/ruvector-gnn/src/error.rs:9-60). */
+#define RUVGNN_OK 0
+#define RUVGNN_ERR_DIMENSION_MISMATCH 1 /* GnnError::DimensionMismatch */
+#define RUVGNN_ERR_INVALID_SHAPE 2      /* GnnError::InvalidShape */
+#define RUVGNN_ERR_LAYER_CONFIG 3       /* GnnError::LayerConfig (layer.rs:101-106,353-358) */
+#define RUVGNN_ERR_INVALID_INPUT 7      /* GnnError::InvalidInput */
+#define RUVGNN_ERR_CUDA 100
+#define RUVGNN_ERR_NCCL 101
+#define RUVGNN_ERR_OOM 102
+
+typedef struct ruvgnn_ctx ruvgnn_ctx;     /* device, stream, workspace */
+typedef struct ruvgnn_layer ruvgnn_layer; /* one RuvectorLayer's weights on the device */
+typedef struct ruvgnn_graph ruvgnn_graph; /* device CSR of one HNSW level */
+
+/* Message of the last failing call on the calling thread (thread-local copy;
+ * for RUVGNN_ERR_LAYER_CONFIG it is the reference's exact text, e.g.
+ * "Dropout must be between 0.0 and 1.0, got 1.5"). */
+const char *ruvgnn_last_error(void);
+
+/* ABI version; bumps on any signature change. */
+uint32_t ruvgnn_abi_version(void);
+
+/* ---- context ----------------------------------------------------------- */
+
+/* `stream` is a cudaStream_t to enqueue on (NULL: the library creates its own).
+ * One forward in flight per ctx.  Replaces nothing in the reference (the CPU
+ * layer has no device state). */
+int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out);
+void ruvgnn_ctx_destroy(ruvgnn_ctx *ctx);
+int32_t ruvgnn_sync(ruvgnn_ctx *ctx);
+void *ruvgnn_ctx_stream(ruvgnn_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *ctx);
+/* Elapsed device milliseconds the last forward spent in each stage
+ * (0 project, 1 aggregate, 2 update, 3 h2d, 4 d2h); needs RUVGNN_FWD_TIMING. */
+int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *ctx, float *ms5);
+
+/* ---- layer: RuvectorLayer::new / serde -------------------------------- */
+
+/* One `Linear` (layer.rs:14-17): weights row-major [out][in] exactly as serde
+ * writes them, bias [out]. */
+typedef struct {
+  const float *w;
+  const float *b;
+} ruvgnn_linear;
+
+/* Field order = serde declaration order: RuvectorLayer (layer.rs:315-333),
+ * GRUCell (:215-227), MultiHeadAttention (:86-93), LayerNorm (:51-55). */
+typedef struct {
+  ruvgnn_linear w_msg, w_agg;
+  ruvgnn_linear w_z, u_z, w_r, u_r, w_h, u_h;
+  ruvgnn_linear q, k, v, out;
+  const float *gamma;
+  const float *beta;
+  float eps; /* 1e-5 in RuvectorLayer::new (layer.rs:365) */
+} ruvgnn_weights;
+
+/* Arithmetic mode of the dense projections.  The gather/aggregate kernel is
+ * always FP32. */
+#define RUVGNN_MODE_FP32_SIMT 0 /* FP32 FFMA GEMMs (any shape; the parity reference on device) */
+#define RUVGNN_MODE_FP32_TC 1   /* tcgen05 3xTF32 error-compensated, FP32 accumulate: FP32-grade */
+#define RUVGNN_MODE_TF32 2      /* tcgen05 single-pass TF32: NOT parity, own tolerance */
+
+/* Replaces RuvectorLayer::new(input_dim, hidden_dim, heads, dropout)
+ * (layer.rs:347-368) with injected weights (host pointers).  Same validation,
+ * same messages: dropout outside [0,1] and hidden_dim % heads != 0
+ * -> RUVGNN_ERR_LAYER_CONFIG. */
+int32_t ruvgnn_layer_create(ruvgnn_ctx *ctx, uint32_t input_dim, uint32_t hidden_dim,
+                            uint32_t heads, float dropout, const ruvgnn_weights *w,
+                            ruvgnn_layer **out);
+/* Validation only (no device needed): what `new` would return. */
+int32_t ruvgnn_layer_validate(uint32_t input_dim, uint32_t hidden_dim, uint32_t heads,
+                              float dropout);
+/* Replaces serde_json::from_str::<RuvectorLayer> (ruvector-gnn-node/src/lib.rs:108-116):
+ * accepts the JSON the reference's to_json() emits. */
+int32_t ruvgnn_layer_from_json(ruvgnn_ctx *ctx, const char *json, size_t len, ruvgnn_layer **out);
+/* Replaces serde_json::to_string(&layer) (lib.rs:97-105).  Writes up to `cap`
+ * bytes (NUL-terminated when it fits) and the needed size (without NUL). */
+int32_t ruvgnn_layer_to_json(const ruvgnn_layer *layer, char *buf, size_t cap, size_t *needed);
+/* Parses a layer JSON and re-emits it in canonical form (same rules as the two calls
+ * above) without touching a device: a validity check for a reference-produced file. */
+int32_t ruvgnn_layer_json_normalize(const char *json, size_t len, char *buf, size_t cap,
+                                    size_t *needed);
+int32_t ruvgnn_layer_dims(const ruvgnn_layer *layer, uint32_t *input_dim, uint32_t *hidden_dim,
+                          uint32_t *heads, float *dropout);
+int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode);
+void ruvgnn_layer_destroy(ruvgnn_layer *layer);
+
+/* ---- graph: HNSW neighbour lists -> device CSR ------------------------- */
+
+/* Packs a list-of-lists of hnsw_rs `Neighbour` records (#[repr(C)]
+ * {d_id: usize, distance: f32, p_id}, patches/hnsw_rs/src/hnsw.rs:97-106) as
+ * returned by Point::get_neighborhood_id()[level] (hnsw.rs:220-240) into CSR.
+ * `lists[i]` points at node i's records (may be NULL when counts[i]==0);
+ * record r of node i lives at lists[i] + r*stride; d_id is read as u64 at
+ * +id_offset and distance as f32 at +dist_offset.  Order is preserved
+ * (ascending distance, hnsw.rs:1186).  row_ptr: [n_nodes+1] u64; col_idx,
+ * edge_w: [sum(counts)].  d_id >= n_nodes or > u32 -> RUVGNN_ERR_INVALID_INPUT.
+ * Host only; no device needed. */
+int32_t ruvgnn_pack_neighbours(uint64_t n_nodes, const void *const *lists, const uint64_t *counts,
+                               size_t stride, size_t id_offset, size_t dist_offset,
+                               uint64_t *row_ptr, uint32_t *col_idx, float *edge_w);
+
+/* Uploads a CSR (host arrays; the caller keeps ownership).  Validates
+ * row_ptr[0]==0, monotone row_ptr, col_idx < n_cols -> RUVGNN_ERR_INVALID_INPUT.
+ * n_cols = number of addressable embedding rows (n_nodes for a single GPU;
+ * n_nodes + n_halo for a partition, see the range-partitioned forward below).
+ * RUVGNN_GRAPH_PRENORMALIZED: edge_w already holds the normalised weights of
+ * layer.rs:426-432 (used by the per-node entry to keep zip truncation). */
+#define RUVGNN_GRAPH_PRENORMALIZED 1u
+int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
+                            const uint64_t *row_ptr, const uint32_t *col_idx, const float *edge_w,
+                            uint32_t flags, ruvgnn_graph **out);
+int32_t ruvgnn_graph_dims(const ruvgnn_graph *g, uint64_t *n_nodes, uint64_t *n_cols,
+                          uint64_t *n_edges);
+/* Copies the device CSR back (bit-exact round-trip check of the upload). */
+int32_t ruvgnn_graph_download(const ruvgnn_graph *g, uint64_t *row_ptr, uint32_t *col_idx,
+                              float *edge_w);
+void ruvgnn_graph_destroy(ruvgnn_graph *g);
+
+/* ---- forward ----------------------------------------------------------- */
+
+#define RUVGNN_FWD_DEVICE_PTRS 1u /* x / out are device pointers (default: host) */
+#define RUVGNN_FWD_ASYNC 2u       /* return after enqueue; ruvgnn_sync() to wait */
+#define RUVGNN_FWD_TIMING 4u      /* record per-stage CUDA events */
+
+/* Batched forward: out[i] = layer.forward(x[i], [x[j] for j in N(i)], w[i])
+ * for every node, all nodes reading the OLD embeddings -- the loop of
+ * verified_training.rs:422-436 / stage_iii.rs:143-168 in one call.
+ * x: [n_nodes][input_dim] row-major, out: [n_nodes][hidden_dim]; must not alias. */
+int32_t ruvgnn_layer_forward(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, const ruvgnn_graph *graph,
+                             const float *x, float *out, uint32_t flags);
+
+/* Replaces RuvectorLayer::forward(&self, node_embedding, neighbor_embeddings,
+ * edge_weights) (layer.rs:379-384) for one node, host buffers.  nbrs is K rows
+ * of x_len floats.  x_len != input_dim -> RUVGNN_ERR_DIMENSION_MISMATCH (the
+ * reference panics inside ndarray).  n_w != K keeps the reference's zip
+ * truncation (layer.rs:438).  Parity/debug entry, not the fast path. */
+int32_t ruvgnn_layer_forward_node(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, const float *x,
+                                  uint32_t x_len, const float *nbrs, uint32_t k, const float *w,
+                                  uint32_t n_w, float *out);
+
+/* ---- range-partitioned forward (one process per GPU) -------- */
+/* Phase A: project the partition's own rows; x is [n_local][input_dim]
+ * (device).  Afterwards ruvgnn_halo_pack gathers the projected K|V|M rows
+ * that peers need. */
+int32_t ruvgnn_layer_project(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, uint64_t n_local,
+                             const float *x_dev);
+/* Gathers rows `idx[0..n_idx)` of the projected K|V|M block into a dense
+ * [n_idx][3*hidden_dim] device buffer (the halo send buffer). */
+int32_t ruvgnn_halo_pack(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, const uint32_t *idx_dev,
+                         uint64_t n_idx, float *send_dev);
+/* Phase B: gather/aggregate + update for local rows [row_begin,row_end).
+ * graph col_idx < n_local address own rows, col_idx >= n_local address
+ * halo_dev[col - n_local] ([n_halo][3*hidden_dim], received from peers). */
+int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
+                                      const ruvgnn_graph *graph, const float *halo_dev,
+                                      uint64_t row_begin, uint64_t row_end, float *out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUVGNN_H */

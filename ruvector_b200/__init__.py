@@ -1,0 +1,16 @@
+"""ruvector_b200 -- B200 (sm_100a) backend for ruvector-gnn's RuvectorLayer forward
+over an HNSW neighbourhood graph.  Host-side mirror of the reference interface over
+the C ABI in include/ruvgnn.h; all arithmetic runs in libruvgnn.so (no CPU fallback).
+"""
+from . import errors
+from .errors import GnnError, LayerConfig, DimensionMismatch, InvalidInput, CudaError
+from .graph import CsrGraph, pack_neighbour_lists, pack_id_distance_lists, batch_to_graph, NEIGHBOUR_DTYPE
+from .layer import Context, DeviceGraph, RuvectorLayer, default_context
+from ._lib import MODE_FP32_SIMT, MODE_FP32_TC, MODE_TF32
+
+__all__ = [
+    "RuvectorLayer", "Context", "DeviceGraph", "CsrGraph", "default_context",
+    "pack_neighbour_lists", "pack_id_distance_lists", "batch_to_graph", "NEIGHBOUR_DTYPE",
+    "GnnError", "LayerConfig", "DimensionMismatch", "InvalidInput", "CudaError", "errors",
+    "MODE_FP32_SIMT", "MODE_FP32_TC", "MODE_TF32",
+]

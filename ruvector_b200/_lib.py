@@ -1,0 +1,97 @@
+"""ctypes binding of libruvgnn.so (include/ruvgnn.h).  No fallback: a missing
+library or a missing GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from .errors import from_status
+
+_LIB_PATH = Path(__file__).resolve().parent / "libruvgnn.so"
+_lib = None
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class Linear(C.Structure):
+    _fields_ = [("w", c_float_p), ("b", c_float_p)]
+
+
+LINEAR_NAMES = ("w_msg", "w_agg", "w_z", "u_z", "w_r", "u_r", "w_h", "u_h", "q", "k", "v", "out")
+
+
+class Weights(C.Structure):
+    """ruvgnn_weights (include/ruvgnn.h)."""
+
+    _fields_ = [(n, Linear) for n in LINEAR_NAMES] + [("gamma", c_float_p), ("beta", c_float_p), ("eps", C.c_float)]
+
+
+# every symbol include/ruvgnn.h declares: name -> (restype, argtypes)
+_vp = C.c_void_p
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+SYMBOLS = {
+    "ruvgnn_last_error": (C.c_char_p, []),
+    "ruvgnn_abi_version": (C.c_uint32, []),
+    "ruvgnn_ctx_create": (C.c_int32, [C.c_int32, _vp, C.POINTER(_vp)]),
+    "ruvgnn_ctx_destroy": (None, [_vp]),
+    "ruvgnn_sync": (C.c_int32, [_vp]),
+    "ruvgnn_ctx_stream": (_vp, [_vp]),
+    "ruvgnn_ctx_launch_count": (C.c_uint64, [_vp]),
+    "ruvgnn_ctx_last_timing": (C.c_int32, [_vp, c_float_p]),
+    "ruvgnn_layer_create": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(Weights), C.POINTER(_vp)]),
+    "ruvgnn_layer_validate": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]),
+    "ruvgnn_layer_from_json": (C.c_int32, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
+    "ruvgnn_layer_to_json": (C.c_int32, [_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ruvgnn_layer_json_normalize": (C.c_int32, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ruvgnn_layer_dims": (C.c_int32, [_vp, _u32p, _u32p, _u32p, c_float_p]),
+    "ruvgnn_layer_set_mode": (C.c_int32, [_vp, C.c_uint32]),
+    "ruvgnn_layer_destroy": (None, [_vp]),
+    "ruvgnn_pack_neighbours": (C.c_int32, [C.c_uint64, C.POINTER(_vp), _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u32p, c_float_p]),
+    "ruvgnn_graph_create": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, _u64p, _u32p, c_float_p, C.c_uint32, C.POINTER(_vp)]),
+    "ruvgnn_graph_dims": (C.c_int32, [_vp, _u64p, _u64p, _u64p]),
+    "ruvgnn_graph_download": (C.c_int32, [_vp, _u64p, _u32p, c_float_p]),
+    "ruvgnn_graph_destroy": (None, [_vp]),
+    "ruvgnn_layer_forward": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32]),
+    "ruvgnn_layer_forward_node": (C.c_int32, [_vp, _vp, c_float_p, C.c_uint32, c_float_p, C.c_uint32, c_float_p, C.c_uint32, c_float_p]),
+    "ruvgnn_layer_project": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
+    "ruvgnn_halo_pack": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "ruvgnn_layer_aggregate_update": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
+}
+
+FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
+GRAPH_PRENORMALIZED = 1
+MODE_FP32_SIMT, MODE_FP32_TC, MODE_TF32 = 0, 1, 2
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Loads libruvgnn.so, failing loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m ruvector_b200.build` "
+            "(or __graft_entry__.build()). ruvector_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().ruvgnn_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int):
+    if status != 0:
+        raise from_status(status, last_error())

@@ -1,0 +1,55 @@
+"""Builds libruvgnn.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension)."""
+from __future__ import annotations
+
+import os
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libruvgnn.so"
+SOURCES = ["ffi.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "rowops.cu", "json.cc", "packer.cc"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source to objects (in parallel) and link the shared library."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "ruvgnn.h"]
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = objdir / (src.rsplit(".", 1)[0] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [CSRC / src] + headers):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(obj), str(CSRC / src)]
+            log = open(objdir / (src + ".log"), "w")
+            procs.append((src, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), log))
+    for src, p, log in procs:
+        rc = p.wait()
+        log.close()
+        if rc != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + (objdir / (src + ".log")).read_text()[-4000:])
+        if verbose:
+            print((objdir / (src + ".log")).read_text())
+    if force or procs or _stale(LIB, objs):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs)]
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

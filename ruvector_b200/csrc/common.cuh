@@ -1,0 +1,125 @@
+// Shared declarations for libruvgnn.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/ruvgnn.h"
+
+namespace ruvgnn {
+
+// ---- error plumbing ------------------------------------------------------
+void set_error(const std::string &msg);
+int32_t fail(int32_t code, const std::string &msg);
+
+#define RUVGNN_CUDA_TRY(expr)                                                             \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      return ::ruvgnn::fail(_e == cudaErrorMemoryAllocation ? RUVGNN_ERR_OOM              \
+                                                            : RUVGNN_ERR_CUDA,            \
+                            std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    }                                                                                     \
+  } while (0)
+
+// ---- the internal column order ("phys") ----------------------------------
+// Every N x H activation the gather kernel touches (Q, K, V, M, o, agg and
+// everything downstream up to the LayerNorm) is stored with its columns
+// permuted so that lane l of a warp owns the logical floats [4P*l, 4P*(l+1))
+// -- i.e. whole heads map to contiguous lane groups -- while each warp-wide
+// 128-bit load still reads 512 contiguous bytes:
+//     logical float4 index f = l*P + i   <->   physical float4 index i*32 + l
+// with P = H/128.  The permutation is folded into the weights once at layer
+// creation, so it costs nothing at run time.  When H % 128 != 0 (or the head
+// count does not divide 32) the order is the identity and the generic kernels run.
+struct ColumnOrder {
+  uint32_t H = 0, P = 0;  // P == 0: identity
+  __host__ __device__ inline uint32_t phys(uint32_t c) const {
+    if (P == 0) return c;
+    uint32_t per_lane = 4 * P;
+    uint32_t lane = c / per_lane, r = c % per_lane;
+    return ((r >> 2) * 32 + lane) * 4 + (r & 3);
+  }
+};
+
+inline bool fast_layout_ok(uint32_t H, uint32_t heads) {
+  if (H % 128 != 0 || heads == 0 || heads > 32 || (32 % heads) != 0) return false;
+  uint32_t P = H / 128;
+  return P == 1 || P == 2 || P == 3 || P == 4 || P == 6 || P == 8;
+}
+
+// ---- GEMM: C[M x N] = [A1 | A2] (M x (K1+K2)) * W^T (W is [N x (K1+K2)]) + epilogue
+enum EpiKind : int {
+  EPI_BIAS = 0,      // out = acc + bias
+  EPI_BIAS_ADD = 1,  // out = acc + bias + add
+  EPI_GATES = 2,     // n <  H: z  = sigmoid(acc+bias)             -> z[row][n]
+                     // n >= H: rh = sigmoid(acc+bias) * m[row][n-H] -> rh[row][n-H]
+  EPI_GRU = 3        // ht = tanh(acc+bias); out = ((1-z)*m + z*ht) * keep
+};
+
+struct GemmArgs {
+  int64_t M = 0;
+  int32_t N = 0, K1 = 0, K2 = 0;
+  const float *A1 = nullptr;
+  int64_t lda1 = 0;
+  const float *A2 = nullptr;
+  int64_t lda2 = 0;
+  const float *W = nullptr;  // [N][K1+K2], row stride K1+K2
+  const float *bias = nullptr;
+  float *out = nullptr;
+  int64_t ldo = 0;
+  const float *add = nullptr;  // EPI_BIAS_ADD
+  int64_t ldadd = 0;
+  const float *m = nullptr;  // EPI_GATES / EPI_GRU: hidden state
+  int64_t ldm = 0;
+  float *z = nullptr;  // EPI_GATES: written; EPI_GRU: read
+  int64_t ldz = 0;
+  float *rh = nullptr;  // EPI_GATES: written
+  int64_t ldrh = 0;
+  int32_t H = 0;
+  float keep = 1.f;  // 1 - dropout
+};
+
+cudaError_t launch_gemm_simt(const GemmArgs &a, EpiKind epi, cudaStream_t s, uint64_t *launches);
+
+// ---- gather / aggregate (K-agg) -------------------------------------------
+struct GatherArgs {
+  const float *P = nullptr;  // [n_local][ldp]: Q | K | V | M (phys order), each H floats
+  int64_t ldp = 0;
+  const float *halo = nullptr;  // [n_halo][3H]: K | V | M of remote rows
+  uint64_t n_local = 0;
+  const uint64_t *row_ptr = nullptr;
+  const uint32_t *col_idx = nullptr;
+  const float *edge_w = nullptr;
+  float *oa = nullptr;  // [n_local][2H]: o | agg
+  uint64_t row_begin = 0, row_end = 0;
+  uint32_t H = 0, heads = 0;
+  int prenormalized = 0;
+};
+cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
+                          uint64_t *launches);
+
+// ---- row ops ----------------------------------------------------------------
+// out[row] = LayerNorm(deg(row) > 0 ? d[row] : m[row]), written in logical order.
+struct LayerNormArgs {
+  const float *d = nullptr;
+  int64_t ldd = 0;
+  const float *m = nullptr;
+  int64_t ldm = 0;
+  const uint64_t *row_ptr = nullptr;  // nullptr: every row takes d
+  const float *gamma = nullptr, *beta = nullptr;  // phys order
+  float eps = 1e-5f;
+  float *out = nullptr;  // [rows][H] logical order
+  uint64_t row_begin = 0, row_end = 0;
+  uint32_t H = 0, P = 0;
+};
+cudaError_t launch_layernorm(const LayerNormArgs &a, cudaStream_t s, uint64_t *launches);
+cudaError_t launch_pack_rows(const float *src, int64_t ld_src, uint32_t row_floats,
+                             const uint32_t *idx, uint64_t n_idx, float *dst, cudaStream_t s,
+                             uint64_t *launches);
+cudaError_t launch_validate_csr(const uint64_t *row_ptr, const uint32_t *col_idx, uint64_t n_nodes,
+                                uint64_t n_cols, uint64_t n_edges, int *d_flag, cudaStream_t s,
+                                uint64_t *launches);
+
+}  // namespace ruvgnn

@@ -1,0 +1,804 @@
+// C ABI of libruvgnn.so (include/ruvgnn.h): context, layer, graph, forward.
+// No CPU fallback anywhere: every compute entry needs a CUDA device.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "layer_host.h"
+
+namespace ruvgnn {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int32_t fail(int32_t code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+}  // namespace ruvgnn
+
+using namespace ruvgnn;
+
+struct ruvgnn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  // activation workspace: P[n][4H] | OA[n][2H] | T0..T3[n][H]
+  float *ws = nullptr;
+  size_t ws_floats = 0;
+  // host-pointer staging
+  float *x_stage = nullptr, *out_stage = nullptr;
+  size_t x_stage_floats = 0, out_stage_floats = 0;
+  int *d_flag = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_ms[5] = {0, 0, 0, 0, 0};
+  bool timing_valid = false;
+  // state of the last ruvgnn_layer_project
+  uint64_t proj_rows = 0;
+  uint32_t proj_H = 0;
+};
+
+struct ruvgnn_layer {
+  LayerHost host;  // logical layout, for to_json and re-upload
+  uint32_t D = 0, H = 0, heads = 0;
+  uint32_t mode = RUVGNN_MODE_FP32_SIMT;
+  bool fast = false;
+  ColumnOrder ord;
+  int device = 0;
+  float *blob = nullptr;  // one allocation, pointers below point inside
+  float *Wmsg = nullptr, *bmsg = nullptr;  // [H][D]
+  float *Wqkv = nullptr, *bqkv = nullptr;  // [3H][H]
+  float *Wo = nullptr, *bo = nullptr;      // [H][H]
+  float *Wagg = nullptr, *bagg = nullptr;  // [H][H]
+  float *Wzr = nullptr, *bzr = nullptr;    // [2H][2H]: rows z|r, cols a|m
+  float *Wh = nullptr, *bh = nullptr;      // [H][2H]: cols a|rh
+  float *gamma = nullptr, *beta = nullptr;
+  TcWeights tc;  // split (hi/lo) copies for the tcgen05 path; empty unless usable
+};
+
+struct ruvgnn_graph {
+  int device = 0;
+  uint64_t n_nodes = 0, n_cols = 0, n_edges = 0;
+  uint32_t flags = 0;
+  uint64_t *row_ptr = nullptr;
+  uint32_t *col_idx = nullptr;
+  float *edge_w = nullptr;
+};
+
+namespace {
+
+int32_t check_config(uint32_t input_dim, uint32_t hidden_dim, uint32_t heads, float dropout) {
+  char buf[160];
+  // RuvectorLayer::new checks dropout first (layer.rs:353-358) ...
+  if (!(dropout >= 0.0f && dropout <= 1.0f)) {
+    snprintf(buf, sizeof buf, "Dropout must be between 0.0 and 1.0, got %g", (double)dropout);
+    return fail(RUVGNN_ERR_LAYER_CONFIG, buf);
+  }
+  // ... then MultiHeadAttention::new the head split (layer.rs:101-106).  heads == 0 is a
+  // division-by-zero panic in the reference; it is reported as the same config error here.
+  if (heads == 0 || hidden_dim % heads != 0) {
+    snprintf(buf, sizeof buf,
+             "Embedding dimension (%u) must be divisible by number of heads (%u)", hidden_dim,
+             heads);
+    return fail(RUVGNN_ERR_LAYER_CONFIG, buf);
+  }
+  if (input_dim == 0 || hidden_dim == 0)
+    return fail(RUVGNN_ERR_INVALID_SHAPE, "input_dim and hidden_dim must be non-zero");
+  return RUVGNN_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      ok = false;
+      prev = -1;
+    }
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    if (!ok) cudaGetLastError();
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int32_t ensure_ws(ruvgnn_ctx *c, uint64_t n, uint32_t H) {
+  const size_t need = (size_t)n * H * 10 + 64;
+  if (need <= c->ws_floats) return RUVGNN_OK;
+  if (c->ws) {
+    RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->ws);
+    c->ws = nullptr;
+    c->ws_floats = 0;
+  }
+  RUVGNN_CUDA_TRY(cudaMalloc(&c->ws, need * sizeof(float)));
+  c->ws_floats = need;
+  return RUVGNN_OK;
+}
+
+int32_t ensure_stage(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
+  if (need <= *have) return RUVGNN_OK;
+  if (*buf) {
+    RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+  }
+  RUVGNN_CUDA_TRY(cudaMalloc(buf, need * sizeof(float)));
+  *have = need;
+  return RUVGNN_OK;
+}
+
+struct Ws {
+  float *P, *OA, *T0, *T1, *T2, *T3;
+  int64_t ldp;
+};
+Ws carve(const ruvgnn_ctx *c, uint64_t n, uint32_t H) {
+  Ws w;
+  w.P = c->ws;
+  w.ldp = 4 * (int64_t)H;
+  w.OA = w.P + (size_t)n * 4 * H;
+  w.T0 = w.OA + (size_t)n * 2 * H;
+  w.T1 = w.T0 + (size_t)n * H;
+  w.T2 = w.T1 + (size_t)n * H;
+  w.T3 = w.T2 + (size_t)n * H;
+  return w;
+}
+
+// One GEMM of the layer, dispatched on the layer's arithmetic mode.
+int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKind epi, int which) {
+  if (L->mode != RUVGNN_MODE_FP32_SIMT && L->tc.usable) {
+    RUVGNN_CUDA_TRY(
+        launch_gemm_tc(g, epi, L->tc, which, L->mode == RUVGNN_MODE_TF32, c->sm_count, c->stream,
+                       &c->launches));
+    return RUVGNN_OK;
+  }
+  RUVGNN_CUDA_TRY(launch_gemm_simt(g, epi, c->stream, &c->launches));
+  return RUVGNN_OK;
+}
+
+// Phase A (K-proj): M = X W_msg^T + b (layer.rs:392-396, once per node instead of once
+// per edge), then Q|K|V = M [W_q;W_k;W_v]^T + b (:135-137).
+int32_t do_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev) {
+  const uint32_t H = L->H, D = L->D;
+  int32_t rc = ensure_ws(c, n, H);
+  if (rc) return rc;
+  Ws w = carve(c, n, H);
+  GemmArgs g;
+  g.M = (int64_t)n;
+  g.N = (int32_t)H;
+  g.K1 = (int32_t)D;
+  g.A1 = x_dev;
+  g.lda1 = D;
+  g.W = L->Wmsg;
+  g.bias = L->bmsg;
+  g.out = w.P + 3 * H;
+  g.ldo = w.ldp;
+  if ((rc = run_gemm(c, L, g, EPI_BIAS, TC_W_MSG))) return rc;
+  GemmArgs q;
+  q.M = (int64_t)n;
+  q.N = (int32_t)(3 * H);
+  q.K1 = (int32_t)H;
+  q.A1 = w.P + 3 * H;
+  q.lda1 = w.ldp;
+  q.W = L->Wqkv;
+  q.bias = L->bqkv;
+  q.out = w.P;
+  q.ldo = w.ldp;
+  if ((rc = run_gemm(c, L, q, EPI_BIAS, TC_W_QKV))) return rc;
+  c->proj_rows = n;
+  c->proj_H = H;
+  return RUVGNN_OK;
+}
+
+// Phase B: K-agg over rows [rb,re), then K-upd (out-proj + combine + W_agg, GRU,
+// dropout scale, LayerNorm; layer.rs:156-159,407-417).
+int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
+                            const float *halo, uint64_t rb, uint64_t re, float *out_dev) {
+  const uint32_t H = L->H;
+  const uint64_t n = c->proj_rows;
+  if (re <= rb) return RUVGNN_OK;
+  Ws w = carve(c, n, H);
+  GatherArgs ga;
+  ga.P = w.P;
+  ga.ldp = w.ldp;
+  ga.halo = halo;
+  ga.n_local = n;
+  ga.row_ptr = G->row_ptr;
+  ga.col_idx = G->col_idx;
+  ga.edge_w = G->edge_w;
+  ga.oa = w.OA;
+  ga.row_begin = rb;
+  ga.row_end = re;
+  ga.H = H;
+  ga.heads = L->heads;
+  ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+  RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
+  if (c->timing_valid) cudaEventRecord(c->ev[3], c->stream);
+
+  const int64_t rows = (int64_t)(re - rb);
+  const float *m = w.P + rb * w.ldp + 3 * H;
+  int32_t rc;
+  {  // combined = W_o o + b_o + agg
+    GemmArgs g;
+    g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H;
+    g.A1 = w.OA + rb * 2 * H; g.lda1 = 2 * H;
+    g.W = L->Wo; g.bias = L->bo;
+    g.add = w.OA + rb * 2 * H + H; g.ldadd = 2 * H;
+    g.out = w.T0 + rb * H; g.ldo = H;
+    if ((rc = run_gemm(c, L, g, EPI_BIAS_ADD, TC_W_O))) return rc;
+  }
+  {  // a = W_agg combined + b_agg
+    GemmArgs g;
+    g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H;
+    g.A1 = w.T0 + rb * H; g.lda1 = H;
+    g.W = L->Wagg; g.bias = L->bagg;
+    g.out = w.T1 + rb * H; g.ldo = H;
+    if ((rc = run_gemm(c, L, g, EPI_BIAS, TC_W_AGG))) return rc;
+  }
+  {  // z = sigma(W_z a + U_z m + b), rh = sigma(W_r a + U_r m + b) * m
+    GemmArgs g;
+    g.M = rows; g.N = (int32_t)(2 * H); g.K1 = (int32_t)H; g.K2 = (int32_t)H;
+    g.A1 = w.T1 + rb * H; g.lda1 = H;
+    g.A2 = m; g.lda2 = w.ldp;
+    g.W = L->Wzr; g.bias = L->bzr;
+    g.m = m; g.ldm = w.ldp;
+    g.z = w.T2 + rb * H; g.ldz = H;
+    g.rh = w.T3 + rb * H; g.ldrh = H;
+    g.H = (int32_t)H;
+    if ((rc = run_gemm(c, L, g, EPI_GATES, TC_W_ZR))) return rc;
+  }
+  {  // d = ((1-z) m + z tanh(W_h a + U_h rh + b)) * (1-p)
+    GemmArgs g;
+    g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H; g.K2 = (int32_t)H;
+    g.A1 = w.T1 + rb * H; g.lda1 = H;
+    g.A2 = w.T3 + rb * H; g.lda2 = H;
+    g.W = L->Wh; g.bias = L->bh;
+    g.m = m; g.ldm = w.ldp;
+    g.z = w.T2 + rb * H; g.ldz = H;
+    g.out = w.T0 + rb * H; g.ldo = H;
+    g.H = (int32_t)H;
+    g.keep = 1.0f - L->host.dropout;
+    if ((rc = run_gemm(c, L, g, EPI_GRU, TC_W_H))) return rc;
+  }
+  LayerNormArgs ln;
+  ln.d = w.T0; ln.ldd = H;
+  ln.m = w.P + 3 * H; ln.ldm = w.ldp;
+  ln.row_ptr = G->row_ptr;
+  ln.gamma = L->gamma; ln.beta = L->beta; ln.eps = L->host.eps;
+  ln.out = out_dev;
+  ln.row_begin = rb; ln.row_end = re;
+  ln.H = H; ln.P = L->ord.P;
+  RUVGNN_CUDA_TRY(launch_layernorm(ln, c->stream, &c->launches));
+  return RUVGNN_OK;
+}
+
+// Builds the device image of a layer: permuted / concatenated weights.
+int32_t upload_layer(ruvgnn_layer *L) {
+  const uint32_t H = L->H, D = L->D;
+  const LayerHost &h = L->host;
+  L->fast = fast_layout_ok(H, L->heads);
+  L->ord.H = H;
+  L->ord.P = L->fast ? H / 128 : 0;
+  const ColumnOrder ord = L->ord;
+  const size_t nW = (size_t)H * D + 3 * (size_t)H * H + 2 * (size_t)H * H + 4 * (size_t)H * H +
+                    2 * (size_t)H * H;
+  const size_t nB = (size_t)H + 3 * H + H + H + 2 * H + H + 2 * H;
+  std::vector<float> blob(nW + nB + 64, 0.f);
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float *p = blob.data() + off;
+    off += (n + 3) & ~(size_t)3;
+    return p;
+  };
+  float *Wmsg = take((size_t)H * D), *bmsg = take(H);
+  float *Wqkv = take(3 * (size_t)H * H), *bqkv = take(3 * H);
+  float *Wo = take((size_t)H * H), *bo = take(H);
+  float *Wagg = take((size_t)H * H), *bagg = take(H);
+  float *Wzr = take(4 * (size_t)H * H), *bzr = take(2 * H);
+  float *Wh = take(2 * (size_t)H * H), *bh = take(H);
+  float *gamma = take(H), *beta = take(H);
+  // rows_perm / cols_perm: does the output / input of this Linear live in phys order?
+  auto place = [&](const HostLinear &l, float *W, size_t ldw, size_t row_off, size_t col_off,
+                   bool cols_perm) {
+    for (uint32_t o = 0; o < l.out; ++o) {
+      float *dst = W + (row_off + ord.phys(o)) * ldw + col_off;
+      const float *src = l.w.data() + (size_t)o * l.in;
+      if (cols_perm)
+        for (uint32_t i = 0; i < l.in; ++i) dst[ord.phys(i)] = src[i];
+      else
+        memcpy(dst, src, sizeof(float) * l.in);
+    }
+  };
+  auto place_b = [&](const HostLinear &l, float *b, size_t row_off, bool accumulate) {
+    for (uint32_t o = 0; o < l.out; ++o) {
+      if (accumulate)
+        b[row_off + ord.phys(o)] += l.b[o];
+      else
+        b[row_off + ord.phys(o)] = l.b[o];
+    }
+  };
+  place(h.lin[L_W_MSG], Wmsg, D, 0, 0, false);
+  place_b(h.lin[L_W_MSG], bmsg, 0, false);
+  place(h.lin[L_Q], Wqkv, H, 0, 0, true);
+  place(h.lin[L_K], Wqkv, H, H, 0, true);
+  place(h.lin[L_V], Wqkv, H, 2 * H, 0, true);
+  place_b(h.lin[L_Q], bqkv, 0, false);
+  place_b(h.lin[L_K], bqkv, H, false);
+  place_b(h.lin[L_V], bqkv, 2 * H, false);
+  place(h.lin[L_OUT], Wo, H, 0, 0, true);
+  place_b(h.lin[L_OUT], bo, 0, false);
+  place(h.lin[L_W_AGG], Wagg, H, 0, 0, true);
+  place_b(h.lin[L_W_AGG], bagg, 0, false);
+  place(h.lin[L_W_Z], Wzr, 2 * H, 0, 0, true);
+  place(h.lin[L_U_Z], Wzr, 2 * H, 0, H, true);
+  place(h.lin[L_W_R], Wzr, 2 * H, H, 0, true);
+  place(h.lin[L_U_R], Wzr, 2 * H, H, H, true);
+  place_b(h.lin[L_W_Z], bzr, 0, false);
+  place_b(h.lin[L_U_Z], bzr, 0, true);
+  place_b(h.lin[L_W_R], bzr, H, false);
+  place_b(h.lin[L_U_R], bzr, H, true);
+  place(h.lin[L_W_H], Wh, 2 * H, 0, 0, true);
+  place(h.lin[L_U_H], Wh, 2 * H, 0, H, true);
+  place_b(h.lin[L_W_H], bh, 0, false);
+  place_b(h.lin[L_U_H], bh, 0, true);
+  for (uint32_t i = 0; i < H; ++i) {
+    gamma[ord.phys(i)] = h.gamma[i];
+    beta[ord.phys(i)] = h.beta[i];
+  }
+  RUVGNN_CUDA_TRY(cudaMalloc(&L->blob, blob.size() * sizeof(float)));
+  RUVGNN_CUDA_TRY(
+      cudaMemcpy(L->blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  auto dev = [&](const float *p) { return L->blob + (p - blob.data()); };
+  L->Wmsg = dev(Wmsg); L->bmsg = dev(bmsg);
+  L->Wqkv = dev(Wqkv); L->bqkv = dev(bqkv);
+  L->Wo = dev(Wo); L->bo = dev(bo);
+  L->Wagg = dev(Wagg); L->bagg = dev(bagg);
+  L->Wzr = dev(Wzr); L->bzr = dev(bzr);
+  L->Wh = dev(Wh); L->bh = dev(bh);
+  L->gamma = dev(gamma); L->beta = dev(beta);
+  // tcgen05 path: split copies (hi/lo) of the six device weight matrices
+  const float *mats[TC_W_COUNT] = {Wmsg, Wqkv, Wo, Wagg, Wzr, Wh};
+  const uint32_t rows[TC_W_COUNT] = {H, 3 * H, H, H, 2 * H, H};
+  const uint32_t cols[TC_W_COUNT] = {D, H, H, H, 2 * H, 2 * H};
+  cudaError_t e = tc_weights_create(mats, rows, cols, &L->tc);
+  if (e != cudaSuccess)
+    return fail(RUVGNN_ERR_CUDA, std::string("tc_weights_create: ") + cudaGetErrorString(e));
+  return RUVGNN_OK;
+}
+
+int32_t make_layer(ruvgnn_ctx *ctx, std::unique_ptr<ruvgnn_layer> L, ruvgnn_layer **out) {
+  int32_t rc = check_config(L->host.input_dim, L->host.hidden_dim, L->host.heads, L->host.dropout);
+  if (rc) return rc;
+  L->D = L->host.input_dim;
+  L->H = L->host.hidden_dim;
+  L->heads = L->host.heads;
+  L->device = ctx->device;
+  DeviceGuard dg(ctx->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  rc = upload_layer(L.get());
+  if (rc) {
+    if (L->blob) cudaFree(L->blob);
+    tc_weights_destroy(&L->tc);
+    return rc;
+  }
+  *out = L.release();
+  return RUVGNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ruvgnn_last_error(void) { return g_last_error.c_str(); }
+uint32_t ruvgnn_abi_version(void) { return 1; }
+
+int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
+  if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(RUVGNN_ERR_CUDA,
+                std::string("no CUDA device available (libruvgnn has no CPU fallback): ") +
+                    cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) return fail(RUVGNN_ERR_INVALID_INPUT, "device out of range");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  RUVGNN_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(RUVGNN_ERR_CUDA, std::string("libruvgnn is built for sm_100a only; device is sm_") +
+                                     std::to_string(prop.major) + std::to_string(prop.minor));
+  std::unique_ptr<ruvgnn_ctx> c(new ruvgnn_ctx());
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    c->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    RUVGNN_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  RUVGNN_CUDA_TRY(cudaMalloc(&c->d_flag, sizeof(int)));
+  for (auto &ev : c->ev) RUVGNN_CUDA_TRY(cudaEventCreate(&ev));
+  *out = c.release();
+  return RUVGNN_OK;
+}
+
+void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
+  if (!c) return;
+  DeviceGuard dg(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->ws) cudaFree(c->ws);
+  if (c->x_stage) cudaFree(c->x_stage);
+  if (c->out_stage) cudaFree(c->out_stage);
+  if (c->d_flag) cudaFree(c->d_flag);
+  for (auto &ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int32_t ruvgnn_sync(ruvgnn_ctx *c) {
+  if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
+  RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RUVGNN_OK;
+}
+void *ruvgnn_ctx_stream(ruvgnn_ctx *c) { return c ? c->stream : nullptr; }
+uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
+
+int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms5) {
+  if (!c || !ms5) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (!c->timing_valid) return fail(RUVGNN_ERR_INVALID_INPUT, "last forward was not timed");
+  RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  // events: 0 start, 1 after h2d, 2 after project, 3 after gather, 4 after update, 5 after d2h
+  float h2d, proj, agg, upd, d2h;
+  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&h2d, c->ev[0], c->ev[1]));
+  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&proj, c->ev[1], c->ev[2]));
+  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, c->ev[2], c->ev[3]));
+  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&upd, c->ev[3], c->ev[4]));
+  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, c->ev[4], c->ev[5]));
+  ms5[0] = proj; ms5[1] = agg; ms5[2] = upd; ms5[3] = h2d; ms5[4] = d2h;
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_validate(uint32_t input_dim, uint32_t hidden_dim, uint32_t heads,
+                              float dropout) {
+  return check_config(input_dim, hidden_dim, heads, dropout);
+}
+
+int32_t ruvgnn_layer_create(ruvgnn_ctx *ctx, uint32_t input_dim, uint32_t hidden_dim,
+                            uint32_t heads, float dropout, const ruvgnn_weights *w,
+                            ruvgnn_layer **out) {
+  if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
+  *out = nullptr;
+  int32_t rc = check_config(input_dim, hidden_dim, heads, dropout);
+  if (rc) return rc;
+  if (!ctx || !w) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx / weights is null");
+  std::unique_ptr<ruvgnn_layer> L(new ruvgnn_layer());
+  LayerHost &h = L->host;
+  h.input_dim = input_dim;
+  h.hidden_dim = hidden_dim;
+  h.heads = heads;
+  h.dropout = dropout;
+  h.eps = w->eps;
+  const ruvgnn_linear *src[L_COUNT] = {&w->w_msg, &w->w_agg, &w->w_z, &w->u_z, &w->w_r, &w->u_r,
+                                       &w->w_h,   &w->u_h,   &w->q,   &w->k,   &w->v,   &w->out};
+  for (int i = 0; i < L_COUNT; ++i) {
+    if (!src[i]->w || !src[i]->b) return fail(RUVGNN_ERR_INVALID_INPUT, "null weight pointer");
+    h.lin[i].out = hidden_dim;
+    h.lin[i].in = (i == L_W_MSG) ? input_dim : hidden_dim;
+    h.lin[i].w.assign(src[i]->w, src[i]->w + (size_t)h.lin[i].out * h.lin[i].in);
+    h.lin[i].b.assign(src[i]->b, src[i]->b + hidden_dim);
+  }
+  if (!w->gamma || !w->beta) return fail(RUVGNN_ERR_INVALID_INPUT, "null gamma/beta");
+  h.gamma.assign(w->gamma, w->gamma + hidden_dim);
+  h.beta.assign(w->beta, w->beta + hidden_dim);
+  return make_layer(ctx, std::move(L), out);
+}
+
+int32_t ruvgnn_layer_from_json(ruvgnn_ctx *ctx, const char *json, size_t len, ruvgnn_layer **out) {
+  if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
+  *out = nullptr;
+  if (!ctx || !json) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx / json is null");
+  std::unique_ptr<ruvgnn_layer> L(new ruvgnn_layer());
+  std::string err = parse_layer_json(json, len, L->host);
+  if (!err.empty()) return fail(RUVGNN_ERR_INVALID_INPUT, err);
+  return make_layer(ctx, std::move(L), out);
+}
+
+int32_t ruvgnn_layer_to_json(const ruvgnn_layer *layer, char *buf, size_t cap, size_t *needed) {
+  if (!layer) return fail(RUVGNN_ERR_INVALID_INPUT, "layer is null");
+  const std::string s = emit_layer_json(layer->host);
+  if (needed) *needed = s.size();
+  if (buf && cap) {
+    const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_json_normalize(const char *json, size_t len, char *buf, size_t cap,
+                                    size_t *needed) {
+  if (!json) return fail(RUVGNN_ERR_INVALID_INPUT, "json is null");
+  LayerHost h;
+  std::string err = parse_layer_json(json, len, h);
+  if (!err.empty()) return fail(RUVGNN_ERR_INVALID_INPUT, err);
+  int32_t rc = check_config(h.input_dim, h.hidden_dim, h.heads, h.dropout);
+  if (rc) return rc;
+  const std::string s = emit_layer_json(h);
+  if (needed) *needed = s.size();
+  if (buf && cap) {
+    const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_dims(const ruvgnn_layer *layer, uint32_t *input_dim, uint32_t *hidden_dim,
+                          uint32_t *heads, float *dropout) {
+  if (!layer) return fail(RUVGNN_ERR_INVALID_INPUT, "layer is null");
+  if (input_dim) *input_dim = layer->D;
+  if (hidden_dim) *hidden_dim = layer->H;
+  if (heads) *heads = layer->heads;
+  if (dropout) *dropout = layer->host.dropout;
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode) {
+  if (!layer) return fail(RUVGNN_ERR_INVALID_INPUT, "layer is null");
+  if (mode > RUVGNN_MODE_TF32) return fail(RUVGNN_ERR_INVALID_INPUT, "unknown mode");
+  if (mode != RUVGNN_MODE_FP32_SIMT && !layer->tc.usable)
+    return fail(RUVGNN_ERR_INVALID_SHAPE,
+                "tensor-core modes need input_dim % 32 == 0 and hidden_dim % 64 == 0");
+  layer->mode = mode;
+  return RUVGNN_OK;
+}
+
+void ruvgnn_layer_destroy(ruvgnn_layer *L) {
+  if (!L) return;
+  DeviceGuard dg(L->device);
+  if (L->blob) cudaFree(L->blob);
+  tc_weights_destroy(&L->tc);
+  delete L;
+}
+
+int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
+                            const uint64_t *row_ptr, const uint32_t *col_idx, const float *edge_w,
+                            uint32_t flags, ruvgnn_graph **out) {
+  if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
+  *out = nullptr;
+  if (!ctx || !row_ptr) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx / row_ptr is null");
+  if (n_cols < n_nodes) return fail(RUVGNN_ERR_INVALID_INPUT, "n_cols < n_nodes");
+  if (n_cols > 0xffffffffull) return fail(RUVGNN_ERR_INVALID_INPUT, "n_cols exceeds u32 col_idx");
+  if (row_ptr[0] != 0) return fail(RUVGNN_ERR_INVALID_INPUT, "row_ptr[0] must be 0");
+  const uint64_t n_edges = row_ptr[n_nodes];
+  if (n_edges && (!col_idx || !edge_w))
+    return fail(RUVGNN_ERR_INVALID_INPUT, "col_idx / edge_w is null");
+  DeviceGuard dg(ctx->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  std::unique_ptr<ruvgnn_graph> g(new ruvgnn_graph());
+  g->device = ctx->device;
+  g->n_nodes = n_nodes;
+  g->n_cols = n_cols;
+  g->n_edges = n_edges;
+  g->flags = flags;
+  auto cleanup = [&]() {
+    if (g->row_ptr) cudaFree(g->row_ptr);
+    if (g->col_idx) cudaFree(g->col_idx);
+    if (g->edge_w) cudaFree(g->edge_w);
+  };
+#define GTRY(expr)                                                                           \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      cleanup();                                                                             \
+      return fail(_e == cudaErrorMemoryAllocation ? RUVGNN_ERR_OOM : RUVGNN_ERR_CUDA,        \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+    }                                                                                        \
+  } while (0)
+  GTRY(cudaMalloc(&g->row_ptr, (n_nodes + 1) * sizeof(uint64_t)));
+  GTRY(cudaMalloc(&g->col_idx, (n_edges + 4) * sizeof(uint32_t)));
+  GTRY(cudaMalloc(&g->edge_w, (n_edges + 4) * sizeof(float)));
+  GTRY(cudaMemcpyAsync(g->row_ptr, row_ptr, (n_nodes + 1) * sizeof(uint64_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  if (n_edges) {
+    GTRY(cudaMemcpyAsync(g->col_idx, col_idx, n_edges * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    GTRY(cudaMemcpyAsync(g->edge_w, edge_w, n_edges * sizeof(float), cudaMemcpyHostToDevice,
+                         ctx->stream));
+  }
+  // device-side validation: monotone row_ptr, col_idx < n_cols
+  GTRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  GTRY(launch_validate_csr(g->row_ptr, g->col_idx, n_nodes, n_cols, n_edges, ctx->d_flag,
+                           ctx->stream, &ctx->launches));
+  int flag = 0;
+  GTRY(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GTRY(cudaStreamSynchronize(ctx->stream));
+#undef GTRY
+  if (flag) {
+    cleanup();
+    return fail(RUVGNN_ERR_INVALID_INPUT,
+                (flag & 1) ? "row_ptr is not monotone non-decreasing"
+                           : "col_idx entry out of range (>= n_cols)");
+  }
+  *out = g.release();
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_graph_dims(const ruvgnn_graph *g, uint64_t *n_nodes, uint64_t *n_cols,
+                          uint64_t *n_edges) {
+  if (!g) return fail(RUVGNN_ERR_INVALID_INPUT, "graph is null");
+  if (n_nodes) *n_nodes = g->n_nodes;
+  if (n_cols) *n_cols = g->n_cols;
+  if (n_edges) *n_edges = g->n_edges;
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_graph_download(const ruvgnn_graph *g, uint64_t *row_ptr, uint32_t *col_idx,
+                              float *edge_w) {
+  if (!g) return fail(RUVGNN_ERR_INVALID_INPUT, "graph is null");
+  DeviceGuard dg(g->device);
+  if (row_ptr)
+    RUVGNN_CUDA_TRY(cudaMemcpy(row_ptr, g->row_ptr, (g->n_nodes + 1) * sizeof(uint64_t),
+                               cudaMemcpyDeviceToHost));
+  if (col_idx && g->n_edges)
+    RUVGNN_CUDA_TRY(
+        cudaMemcpy(col_idx, g->col_idx, g->n_edges * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (edge_w && g->n_edges)
+    RUVGNN_CUDA_TRY(
+        cudaMemcpy(edge_w, g->edge_w, g->n_edges * sizeof(float), cudaMemcpyDeviceToHost));
+  return RUVGNN_OK;
+}
+
+void ruvgnn_graph_destroy(ruvgnn_graph *g) {
+  if (!g) return;
+  DeviceGuard dg(g->device);
+  if (g->row_ptr) cudaFree(g->row_ptr);
+  if (g->col_idx) cudaFree(g->col_idx);
+  if (g->edge_w) cudaFree(g->edge_w);
+  delete g;
+}
+
+int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
+                             const float *x, float *out, uint32_t flags) {
+  if (!c || !L || !G || !x || !out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (L->device != c->device || G->device != c->device)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "layer / graph live on another device than ctx");
+  if (G->n_cols != G->n_nodes)
+    return fail(RUVGNN_ERR_INVALID_INPUT,
+                "graph addresses halo rows; use ruvgnn_layer_aggregate_update");
+  const uint64_t n = G->n_nodes;
+  if (n == 0) return RUVGNN_OK;
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
+  const bool timing = flags & RUVGNN_FWD_TIMING;
+  const float *x_dev = x;
+  float *out_dev = out;
+  int32_t rc;
+  c->timing_valid = false;
+  if (!dev_ptrs) {
+    if ((rc = ensure_stage(c, &c->x_stage, &c->x_stage_floats, (size_t)n * L->D))) return rc;
+    if ((rc = ensure_stage(c, &c->out_stage, &c->out_stage_floats, (size_t)n * L->H))) return rc;
+    x_dev = c->x_stage;
+    out_dev = c->out_stage;
+  } else if (x == out) {
+    return fail(RUVGNN_ERR_INVALID_INPUT, "out must not alias x (Jacobi update)");
+  }
+  if ((rc = ensure_ws(c, n, L->H))) return rc;
+  if (timing) {
+    c->timing_valid = true;
+    cudaEventRecord(c->ev[0], c->stream);
+  }
+  if (!dev_ptrs)
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(c->x_stage, x, (size_t)n * L->D * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->stream));
+  if (timing) cudaEventRecord(c->ev[1], c->stream);
+  if ((rc = do_project(c, L, n, x_dev))) return rc;
+  if (timing) cudaEventRecord(c->ev[2], c->stream);
+  if ((rc = do_aggregate_update(c, L, G, nullptr, 0, n, out_dev))) return rc;
+  if (timing) cudaEventRecord(c->ev[4], c->stream);
+  if (!dev_ptrs)
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(out, c->out_stage, (size_t)n * L->H * sizeof(float),
+                                    cudaMemcpyDeviceToHost, c->stream));
+  if (timing) cudaEventRecord(c->ev[5], c->stream);
+  if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_forward_node(ruvgnn_ctx *c, const ruvgnn_layer *L, const float *x,
+                                  uint32_t x_len, const float *nbrs, uint32_t k, const float *w,
+                                  uint32_t n_w, float *out) {
+  if (!c || !L || !x || !out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (x_len != L->D) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "Tensor dimension mismatch: expected %u, got %u", L->D, x_len);
+    return fail(RUVGNN_ERR_DIMENSION_MISMATCH, buf);
+  }
+  if (k && !nbrs) return fail(RUVGNN_ERR_INVALID_INPUT, "nbrs is null");
+  if (n_w && !w) return fail(RUVGNN_ERR_INVALID_INPUT, "edge weights are null");
+  const uint32_t D = L->D, H = L->H;
+  // rows: 0 = the node, 1..k = its neighbours (no out-edges: their outputs are discarded)
+  std::vector<float> X((size_t)(k + 1) * D);
+  memcpy(X.data(), x, sizeof(float) * D);
+  if (k) memcpy(X.data() + D, nbrs, sizeof(float) * (size_t)k * D);
+  std::vector<uint64_t> rp(k + 2, k);
+  rp[0] = 0;
+  std::vector<uint32_t> col(k ? k : 1);
+  for (uint32_t j = 0; j < k; ++j) col[j] = j + 1;
+  // aggregate_messages' normalisation incl. zip truncation (layer.rs:421-445), done on the
+  // host in the reference's order so n_w != k behaves identically.
+  std::vector<float> nw(k ? k : 1, 0.f);
+  if (k && n_w) {
+    float wsum = 0.f;
+    for (uint32_t j = 0; j < n_w; ++j) wsum = wsum + w[j];
+    const uint32_t lim = k < n_w ? k : n_w;
+    for (uint32_t j = 0; j < lim; ++j) nw[j] = wsum > 0.f ? w[j] / wsum : 1.0f / (float)n_w;
+  }
+  ruvgnn_graph *g = nullptr;
+  int32_t rc = ruvgnn_graph_create(c, k + 1, k + 1, rp.data(), col.data(), nw.data(),
+                                   RUVGNN_GRAPH_PRENORMALIZED, &g);
+  if (rc) return rc;
+  std::vector<float> O((size_t)(k + 1) * H);
+  rc = ruvgnn_layer_forward(c, L, g, X.data(), O.data(), 0);
+  ruvgnn_graph_destroy(g);
+  if (rc) return rc;
+  memcpy(out, O.data(), sizeof(float) * H);
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_local,
+                             const float *x_dev) {
+  if (!c || !L || !x_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  c->timing_valid = false;
+  return do_project(c, L, n_local, x_dev);
+}
+
+int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *idx_dev,
+                         uint64_t n_idx, float *send_dev) {
+  if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (n_idx == 0) return RUVGNN_OK;
+  if (!idx_dev || !send_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (c->proj_rows == 0 || c->proj_H != L->H)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "ruvgnn_layer_project has not run for this layer");
+  DeviceGuard dg(c->device);
+  Ws w = carve(c, c->proj_rows, L->H);
+  RUVGNN_CUDA_TRY(launch_pack_rows(w.P + L->H, w.ldp, 3 * L->H, idx_dev, n_idx, send_dev,
+                                   c->stream, &c->launches));
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
+                                      const float *halo_dev, uint64_t row_begin, uint64_t row_end,
+                                      float *out_dev) {
+  if (!c || !L || !G || !out_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (c->proj_rows != G->n_nodes || c->proj_H != L->H)
+    return fail(RUVGNN_ERR_INVALID_INPUT,
+                "ruvgnn_layer_project must run first with n_local == graph rows");
+  if (G->n_cols > G->n_nodes && !halo_dev)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "graph addresses halo rows but halo_dev is null");
+  if (row_end > G->n_nodes || row_begin > row_end)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "row range out of bounds");
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  c->timing_valid = false;
+  return do_aggregate_update(c, L, G, halo_dev, row_begin, row_end, out_dev);
+}
+
+}  // extern "C"

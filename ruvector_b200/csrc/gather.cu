@@ -1,0 +1,289 @@
+// K-agg: neighbour gather + per-head scaled-dot-product softmax aggregation
+// + edge-weight aggregation, one warp per node.  HBM-bound.
+//
+// Replaces, for every node at once (reference: crates/ruvector-gnn/src/layer.rs):
+//   split_heads :163-171 + scaled_dot_product_attention :174-210   -> o   (pre W_o)
+//   aggregate_messages :421-445                                     -> agg
+// Inputs are the projected rows Q | K | V | M written by the projection GEMMs.
+// Per edge the kernel reads ONE contiguous 3H-float block (K_j | V_j | M_j):
+// formulation R = 3 of SURVEY.md 8(d); algorithmic bytes per node
+//   4H (Q) + 16 (row_ptr pair) + deg*(4 + 4 + 12H) + 8H (o, agg).
+//
+// Softmax is the online (running max / running sum) form so any degree works
+// in one pass; it equals the reference's max-subtracted softmax up to f32
+// rounding.  sum.max(1e-10) (:198) is kept.
+#include "common.cuh"
+
+namespace ruvgnn {
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Normalised-weight rule of aggregate_messages (:426-432), per edge.
+struct WeightRule {
+  float wsum;
+  float uniform;  // 1/len(w)
+  int mode;       // 0: w / wsum, 1: uniform, 2: already normalised
+  __device__ __forceinline__ float apply(float w) const {
+    return mode == 0 ? w / wsum : (mode == 1 ? uniform : w);
+  }
+};
+
+__device__ __forceinline__ WeightRule make_rule(const float *edge_w, uint64_t beg, uint64_t end,
+                                                int lane, int prenormalized) {
+  WeightRule r;
+  r.wsum = 1.f;
+  r.uniform = 1.0f / (float)(end - beg);
+  if (prenormalized) {
+    r.mode = 2;
+    return r;
+  }
+  float s = 0.f;
+  for (uint64_t e = beg + lane; e < end; e += 32) s += __ldg(edge_w + e);
+  s = warp_sum(s);
+  r.wsum = s;
+  r.mode = s > 0.f ? 0 : 1;
+  return r;
+}
+
+template <int P>
+struct RowRegs {
+  float4 k[P], v[P], m[P];
+};
+
+// P = H/128 float4 per lane per row; LH = 32/heads lanes per head; U = edges in flight.
+template <int P, int LH, int U>
+__global__ void __launch_bounds__(128) gather_fast_kernel(GatherArgs a, float inv_scale) {
+  constexpr int H = 128 * P;
+  constexpr int V = 32 * P;  // float4 per H-row
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+
+  for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
+    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    float4 *orow = reinterpret_cast<float4 *>(a.oa + node * (uint64_t)(2 * H));
+    if (beg == end) {  // no neighbours: the update kernel takes the LN(m) path (:385-389)
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 2 * P; ++i) orow[i * 32 + lane] = zero;
+      continue;
+    }
+    const float4 *qrow = reinterpret_cast<const float4 *>(a.P + node * (uint64_t)a.ldp);
+    float4 q[P], acc[P], ag[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      q[i] = ldg4(qrow + i * 32 + lane);
+      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
+    float mx = -INFINITY, l = 0.f;
+
+    auto row_of = [&](uint32_t col) -> const float4 * {
+      return (uint64_t)col < a.n_local
+                 ? reinterpret_cast<const float4 *>(a.P + (uint64_t)col * a.ldp + H)
+                 : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * (3 * H));
+    };
+    auto load = [&](RowRegs<P> &r, const float4 *rp) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) r.k[i] = ldg4(rp + i * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < P; ++i) r.v[i] = ldg4(rp + V + i * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < P; ++i) r.m[i] = ldg4(rp + 2 * V + i * 32 + lane);
+    };
+    auto consume = [&](const RowRegs<P> &r, float what) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        part = fmaf(q[i].x, r.k[i].x, part);
+        part = fmaf(q[i].y, r.k[i].y, part);
+        part = fmaf(q[i].z, r.k[i].z, part);
+        part = fmaf(q[i].w, r.k[i].w, part);
+      }
+#pragma unroll
+      for (int o = LH / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const float s = part * inv_scale;  // dot / sqrt(head_dim)  (:184-191)
+      const float mnew = fmaxf(mx, s);
+      const float corr = expf(mx - mnew);
+      const float p = expf(s - mnew);
+      l = fmaf(l, corr, p);
+      mx = mnew;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        acc[i].x = fmaf(acc[i].x, corr, p * r.v[i].x);
+        acc[i].y = fmaf(acc[i].y, corr, p * r.v[i].y);
+        acc[i].z = fmaf(acc[i].z, corr, p * r.v[i].z);
+        acc[i].w = fmaf(acc[i].w, corr, p * r.v[i].w);
+        ag[i].x = fmaf(what, r.m[i].x, ag[i].x);
+        ag[i].y = fmaf(what, r.m[i].y, ag[i].y);
+        ag[i].z = fmaf(what, r.m[i].z, ag[i].z);
+        ag[i].w = fmaf(what, r.m[i].w, ag[i].w);
+      }
+    };
+
+    for (uint64_t c = beg; c < end; c += 32) {
+      const uint64_t e = c + lane;
+      const uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      const float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
+      const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
+      int jj = 0;
+      for (; jj + U <= cnt; jj += U) {
+        RowRegs<P> r[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t col = __shfl_sync(0xffffffffu, my_col, jj + u);
+          w[u] = __shfl_sync(0xffffffffu, my_w, jj + u);
+          load(r[u], row_of(col));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(r[u], w[u]);
+      }
+      for (; jj < cnt; ++jj) {
+        RowRegs<P> r;
+        const uint32_t col = __shfl_sync(0xffffffffu, my_col, jj);
+        const float w = __shfl_sync(0xffffffffu, my_w, jj);
+        load(r, row_of(col));
+        consume(r, w);
+      }
+    }
+    const float inv_l = 1.0f / fmaxf(l, 1e-10f);  // sum_exp.max(1e-10) (:198)
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      orow[i * 32 + lane] =
+          make_float4(acc[i].x * inv_l, acc[i].y * inv_l, acc[i].z * inv_l, acc[i].w * inv_l);
+      orow[V + i * 32 + lane] = ag[i];
+    }
+  }
+}
+
+// Any H / head count (identity column order).  One warp per node, running
+// state in shared memory.  Correctness path for shapes the fast kernel does
+// not cover (e.g. the reference's 4->8, 2-head unit-test layer).
+__global__ void gather_generic_kernel(GatherArgs a, float inv_scale) {
+  extern __shared__ float sm[];
+  const int H = (int)a.H, h = (int)a.heads, dh = H / h;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float *q = sm + (size_t)wib * (3 * H + 2 * h);
+  float *acc = q + H, *ag = acc + H, *mxs = ag + H, *ls = mxs + h;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
+    const uint64_t beg = a.row_ptr[node], end = a.row_ptr[node + 1];
+    float *orow = a.oa + node * (uint64_t)(2 * H);
+    if (beg == end) {
+      for (int t = lane; t < 2 * H; t += 32) orow[t] = 0.f;
+      continue;
+    }
+    const float *qrow = a.P + node * (uint64_t)a.ldp;
+    for (int t = lane; t < H; t += 32) {
+      q[t] = qrow[t];
+      acc[t] = 0.f;
+      ag[t] = 0.f;
+    }
+    for (int g = lane; g < h; g += 32) {
+      mxs[g] = -INFINITY;
+      ls[g] = 0.f;
+    }
+    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
+    __syncwarp();
+    for (uint64_t e = beg; e < end; ++e) {
+      const uint64_t col = a.col_idx[e];
+      const float what = rule.apply(a.edge_w[e]);
+      const float *rp = col < a.n_local ? a.P + col * (uint64_t)a.ldp + H
+                                        : a.halo + (col - a.n_local) * (uint64_t)(3 * H);
+      const float *kr = rp, *vr = rp + H, *mr = rp + 2 * H;
+      for (int g = 0; g < h; ++g) {
+        float part = 0.f;
+        for (int t = lane; t < dh; t += 32) part = fmaf(q[g * dh + t], kr[g * dh + t], part);
+        part = warp_sum(part);
+        const float s = part * inv_scale;
+        const float mold = mxs[g], lold = ls[g];
+        const float mnew = fmaxf(mold, s);
+        const float corr = expf(mold - mnew), p = expf(s - mnew);
+        for (int t = lane; t < dh; t += 32)
+          acc[g * dh + t] = fmaf(acc[g * dh + t], corr, p * vr[g * dh + t]);
+        __syncwarp();
+        if (lane == 0) {
+          mxs[g] = mnew;
+          ls[g] = fmaf(lold, corr, p);
+        }
+      }
+      for (int t = lane; t < H; t += 32) ag[t] = fmaf(what, mr[t], ag[t]);
+      __syncwarp();
+    }
+    for (int t = lane; t < H; t += 32) {
+      orow[t] = acc[t] * (1.0f / fmaxf(ls[t / dh], 1e-10f));
+      orow[H + t] = ag[t];
+    }
+    __syncwarp();
+  }
+}
+
+template <int P, int U>
+cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cudaStream_t s) {
+  const uint64_t rows = a.row_end - a.row_begin;
+  const int wpb = 4;
+  uint64_t blocks = (rows + wpb - 1) / wpb;
+  // grid-stride: a few resident waves, a multiple of the SM count
+  const uint64_t cap = (uint64_t)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  dim3 grid((unsigned)blocks), block(32 * wpb);
+  switch (32 / a.heads) {
+    case 32: gather_fast_kernel<P, 32, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 16: gather_fast_kernel<P, 16, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 8: gather_fast_kernel<P, 8, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 4: gather_fast_kernel<P, 4, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 2: gather_fast_kernel<P, 2, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 1: gather_fast_kernel<P, 1, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
+                          uint64_t *launches) {
+  if (a.row_end <= a.row_begin) return cudaSuccess;
+  const float inv_scale = 1.0f / sqrtf((float)(a.H / a.heads));
+  if (launches) ++*launches;
+  if (fast) {
+    switch (a.H / 128) {
+      case 1: return launch_fast_p<1, 4>(a, inv_scale, sm_count, s);
+      case 2: return launch_fast_p<2, 2>(a, inv_scale, sm_count, s);
+      case 3: return launch_fast_p<3, 2>(a, inv_scale, sm_count, s);
+      case 4: return launch_fast_p<4, 1>(a, inv_scale, sm_count, s);
+      case 6: return launch_fast_p<6, 1>(a, inv_scale, sm_count, s);
+      case 8: return launch_fast_p<8, 1>(a, inv_scale, sm_count, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  const size_t per_warp = (size_t)(3 * a.H + 2 * a.heads) * sizeof(float);
+  int wpb = (int)((size_t)(96 * 1024) / per_warp);
+  if (wpb > 4) wpb = 4;
+  if (wpb < 1) wpb = 1;
+  const size_t smem = per_warp * wpb;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gather_generic_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const uint64_t rows = a.row_end - a.row_begin;
+  uint64_t blocks = (rows + wpb - 1) / wpb;
+  const uint64_t cap = (uint64_t)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  gather_generic_kernel<<<(unsigned)blocks, 32 * wpb, smem, s>>>(a, inv_scale);
+  return cudaGetLastError();
+}
+
+}  // namespace ruvgnn

@@ -1,0 +1,217 @@
+"""Pins the CPU oracle (oracle/ruvgnn_oracle.c).
+
+The reference has no golden vectors for this path and cannot be
+built here, so the restatement is pinned by: an independent NumPy twin, hand-derived
+closed forms, and every property the reference's own tests assert
+(crates/ruvector-gnn/src/layer.rs:459-546, crates/ruvector-gnn-node/test/basic.test.js:54-73,
+crates/ruvector-gnn/src/search.rs:164-247).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ruvector_b200 as rv
+from oracle import oracle_np
+from ruvector_b200 import synth
+from ruvector_b200._lib import c_float_p
+
+F32 = np.float32
+
+
+def _p(a):
+    return a.ctypes.data_as(c_float_p)
+
+
+def rel_rows(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-6)
+
+
+def identity_weights(d, h_bias=0.0):
+    eye = np.eye(d, dtype=F32)
+    w = {n: (eye.copy(), np.full(d, h_bias, dtype=F32)) for n in synth.LINEARS}
+    w["gamma"] = np.ones(d, dtype=F32)
+    w["beta"] = np.zeros(d, dtype=F32)
+    w["eps"] = 1e-5
+    return w
+
+
+# ---- reference unit-test properties (layer.rs:459-546) -------------------------
+
+def test_linear_shape_and_value(oracle):
+    w = np.arange(8, dtype=F32).reshape(2, 4)
+    b = np.array([0.5, -1.0], dtype=F32)
+    x = np.array([1, 2, 3, 4], dtype=F32)
+    y = np.empty(2, dtype=F32)
+    oracle.lib.orc_linear_forward(_p(w), _p(b), 4, 2, _p(x), _p(y))
+    assert y.tolist() == [20.5, 59.0]  # exact small integers
+
+
+def test_layer_norm_zero_mean(oracle):  # layer.rs:472-480
+    g, b = np.ones(4, dtype=F32), np.zeros(4, dtype=F32)
+    x = np.array([1, 2, 3, 4], dtype=F32)
+    y = np.empty(4, dtype=F32)
+    oracle.lib.orc_layernorm_forward(_p(g), _p(b), 1e-5, 4, _p(x), _p(y))
+    assert abs(float(y.mean())) < 1e-5
+    # closed form: var = 1.25
+    expect = (x - 2.5) / np.sqrt(F32(1.25) + F32(1e-5))
+    np.testing.assert_allclose(y, expect, rtol=1e-6)
+
+
+def test_sigmoid_branches(oracle):  # layer.rs:278-285
+    for v in (-30.0, -1.5, 0.0, 1.5, 30.0):
+        assert abs(oracle.lib.orc_sigmoid(v) - 1.0 / (1.0 + np.exp(-v))) < 1e-7
+
+
+def test_output_length_with_and_without_neighbours(oracle):  # layer.rs:512-533
+    layer = rv.RuvectorLayer(4, 8, 2, 0.1, rng=np.random.default_rng(1))
+    node = np.array([1, 2, 3, 4], dtype=F32)
+    nb = np.array([[0.5, 1.0, 1.5, 2.0], [2.0, 3.0, 4.0, 5.0]], dtype=F32)
+    out = oracle.forward_node(layer, node, nb, [0.3, 0.7])
+    assert out.shape == (8,) and np.isfinite(out).all()
+    out0 = oracle.forward_node(layer, node, np.zeros((0, 4), F32), [])
+    assert out0.shape == (8,) and abs(float(out0.mean())) < 1e-5
+
+
+# ---- hand-derived closed forms ------------------------------------------------
+
+def test_no_neighbours_is_layernorm_of_projection(oracle):
+    d, hdim = 6, 8
+    w = synth.make_weights(d, hdim, seed=3)
+    layer = rv.RuvectorLayer(d, hdim, 2, 0.25, weights=w)
+    x = synth.make_features(1, d, seed=9)[0]
+    m = (w["w_msg"][0].astype(np.float64) @ x + w["w_msg"][1]).astype(np.float64)
+    mu, var = m.mean(), m.var()
+    expect = (m - mu) / np.sqrt(var + 1e-5) * w["gamma"] + w["beta"]
+    out = oracle.forward_node(layer, x, np.zeros((0, d), F32), [])
+    np.testing.assert_allclose(out, expect, rtol=2e-5, atol=2e-6)
+
+
+def test_identity_layer_single_neighbour_closed_form(oracle):
+    """D=H=2, one head, identity weights, zero biases, one neighbour n, node x:
+    m=x, attention over one key = v = n, agg = n (w/w = 1), a = 2n,
+    z = s(2n+x), r = s(2n+x), h~ = tanh(2n + r*x), h' = (1-z)x + z h~, out = LN(0.5 h')."""
+    layer = rv.RuvectorLayer(2, 2, 1, 0.5, weights=identity_weights(2))
+    x = np.array([0.3, -0.7], dtype=np.float64)
+    n = np.array([0.9, 0.2], dtype=np.float64)
+    s = lambda t: 1 / (1 + np.exp(-t))
+    z = s(2 * n + x)
+    r = s(2 * n + x)
+    ht = np.tanh(2 * n + r * x)
+    h = ((1 - z) * x + z * ht) * 0.5
+    expect = (h - h.mean()) / np.sqrt(h.var() + 1e-5)
+    out = oracle.forward_node(layer, x.astype(F32), n.astype(F32)[None, :], [0.37])
+    np.testing.assert_allclose(out, expect, rtol=1e-5, atol=1e-6)
+
+
+def test_equal_scores_give_uniform_attention(oracle):
+    """Zero query projection => all scores equal => attention = mean of the values."""
+    d = 8
+    w = synth.make_weights(d, d, seed=5)
+    w["q"] = (np.zeros((d, d), F32), np.zeros(d, F32))
+    layer = rv.RuvectorLayer(d, d, 2, 0.0, weights=w)
+    x = synth.make_features(4, d, seed=11)
+    out = oracle.forward_node(layer, x[0], x[1:], [1.0, 1.0, 1.0])
+    # numpy twin computes the general formula; uniform attention must coincide with it
+    g = rv.CsrGraph(np.array([0, 3, 3, 3, 3], np.uint64), np.array([1, 2, 3], np.uint32), np.ones(3, F32))
+    ref = oracle_np.forward_graph(w, d, d, 2, 0.0, x, g.row_ptr, g.col_idx, g.edge_w)[0]
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-6)
+    # and explicitly: attn = W_o mean(v) + b_o
+    m = x @ w["w_msg"][0].T + w["w_msg"][1]
+    v = m[1:] @ w["v"][0].T + w["v"][1]
+    attn = v.mean(axis=0) @ w["out"][0].T + w["out"][1]
+    assert np.isfinite(attn).all()
+
+
+def test_nonpositive_weight_sum_is_uniform(oracle):  # layer.rs:428-432
+    d = 8
+    layer = rv.RuvectorLayer(d, d, 2, 0.1, weights=synth.make_weights(d, d, seed=6))
+    x = synth.make_features(4, d, seed=12)
+    a = oracle.forward_node(layer, x[0], x[1:], [-0.5, -0.2, -0.1])  # DotProduct-style negative distances
+    b = oracle.forward_node(layer, x[0], x[1:], [1.0, 1.0, 1.0])
+    np.testing.assert_allclose(a, b, rtol=0, atol=0)
+    c = oracle.forward_node(layer, x[0], x[1:], [0.0, 0.0, 0.0])
+    np.testing.assert_array_equal(a, c)
+
+
+def test_zip_truncation_of_edge_weights(oracle):  # layer.rs:438
+    d = 8
+    layer = rv.RuvectorLayer(d, d, 2, 0.1, weights=synth.make_weights(d, d, seed=7))
+    x = synth.make_features(4, d, seed=13)
+    # fewer weights than neighbours: the third message gets no weight, normaliser = w0+w1
+    short = oracle.forward_node(layer, x[0], x[1:], [0.2, 0.6])
+    # equivalent: three weights with the last one zero
+    full = oracle.forward_node(layer, x[0], x[1:], [0.2, 0.6, 0.0])
+    np.testing.assert_array_equal(short, full)
+    # empty weights: aggregation is zero but attention still sees 3 keys
+    none = oracle.forward_node(layer, x[0], x[1:], [])
+    assert np.isfinite(none).all() and not np.array_equal(none, short)
+
+
+# ---- C oracle vs independent NumPy twin ------------------------------------------
+
+@pytest.mark.parametrize("n,d,hdim,heads,m", [(300, 16, 16, 4, 4), (257, 12, 24, 3, 5), (200, 128, 128, 4, 8),
+                                                (120, 48, 96, 8, 6)])
+def test_c_oracle_matches_numpy_twin(oracle, n, d, hdim, heads, m):
+    w = synth.make_weights(d, hdim, seed=100 + n)
+    layer = rv.RuvectorLayer(d, hdim, heads, 0.1, weights=w)
+    x = synth.make_features(n, d, seed=n)
+    g = synth.hnsw_like_graph(n, m, seed=n + 1, iso_frac=0.05)
+    c_out = oracle.forward_graph(layer, x, g)
+    np_out = oracle_np.forward_graph(w, d, hdim, heads, 0.1, x, g.row_ptr, g.col_idx, g.edge_w)
+    assert rel_rows(c_out, np_out).max() < 5e-6
+    assert np.abs(c_out - np_out).max() < 2e-5
+
+
+def test_faithful_and_cached_drivers_are_bit_identical(oracle):
+    n, d = 150, 32
+    layer = rv.RuvectorLayer(d, d, 4, 0.1, weights=synth.make_weights(d, d, seed=21))
+    x = synth.make_features(n, d, seed=22)
+    g = synth.hnsw_like_graph(n, 6, seed=23, iso_frac=0.05)
+    a = oracle.forward_graph(layer, x, g, faithful=True, threads=3)
+    b = oracle.forward_graph(layer, x, g, threads=2)
+    np.testing.assert_array_equal(a, b)
+    # and both equal the per-node entry
+    i = int(np.argmax(g.degrees()))
+    s, e = int(g.row_ptr[i]), int(g.row_ptr[i + 1])
+    one = oracle.forward_node(layer, x[i], x[g.col_idx[s:e]], g.edge_w[s:e])
+    np.testing.assert_array_equal(one, a[i])
+
+
+def test_json_roundtrip_gives_identical_forward(oracle):  # basic.test.js:54-73 (tolerance 1e-6 there)
+    layer = rv.RuvectorLayer(4, 8, 2, 0.1, rng=np.random.default_rng(3))
+    again = rv.RuvectorLayer.from_json(layer.to_json())
+    node = np.array([1, 2, 3, 4], dtype=F32)
+    nb = np.array([[0.5, 1.0, 1.5, 2.0], [2.0, 3.0, 4.0, 5.0]], dtype=F32)
+    a = oracle.forward_node(layer, node, nb, [0.3, 0.7])
+    b = oracle.forward_node(again, node, nb, [0.3, 0.7])
+    np.testing.assert_array_equal(a, b)
+
+
+# ---- search.rs restatement (search.rs:164-247) ------------------------------------
+
+def test_cosine_similarity(oracle):
+    a = np.array([1, 2, 3], dtype=F32)
+    assert abs(oracle.lib.orc_cosine_similarity(_p(a), _p(a), 3) - 1.0) < 1e-6
+    b = np.array([1, 0, 0], dtype=F32)
+    c = np.array([0, 1, 0], dtype=F32)
+    assert abs(oracle.lib.orc_cosine_similarity(_p(b), _p(c), 3)) < 1e-6
+
+
+def test_softmax_sums_to_one_and_is_monotone(oracle):
+    v = np.array([1, 2, 3], dtype=F32)
+    out = np.empty(3, dtype=F32)
+    oracle.lib.orc_softmax_t(_p(v), 3, 1.0, _p(out))
+    assert abs(float(out.sum()) - 1.0) < 1e-6 and out[0] < out[1] < out[2]
+    sharp = np.empty(3, dtype=F32)
+    oracle.lib.orc_softmax_t(_p(v), 3, 0.1, _p(sharp))
+    assert sharp[2] > out[2]
+
+
+def test_differentiable_search_top1(oracle):  # search.rs:206-225
+    q = np.array([1, 0, 0], dtype=F32)
+    cands = np.array([[1, 0, 0], [0.9, 0.1, 0], [0, 1, 0]], dtype=F32)
+    idx = np.empty(2, dtype=np.uint32)
+    wts = np.empty(2, dtype=F32)
+    k = oracle.lib.orc_differentiable_search(_p(q), _p(cands), 3, 3, 2, 1.0, idx.ctypes.data_as(C.POINTER(C.c_uint32)), _p(wts))
+    assert k == 2 and idx[0] == 0 and idx[1] == 1 and wts[0] > wts[1]
