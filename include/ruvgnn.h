@@ -58,8 +58,9 @@ int32_t ruvgnn_sync(ruvgnn_ctx *ctx);
 void *ruvgnn_ctx_stream(ruvgnn_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *ctx);
-/* Elapsed device milliseconds the last forward spent in each stage
- * (0 project, 1 aggregate, 2 update, 3 h2d, 4 d2h); needs RUVGNN_FWD_TIMING. */
+/* Device milliseconds per stage (0 project, 1 aggregate, 2 update, 3 h2d, 4 d2h),
+ * averaged over the RUVGNN_FWD_TIMING forwards (up to 32) since the previous query;
+ * CUDA events on the launching stream.  Synchronises the stream. */
 int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *ctx, float *ms5);
 
 /* ---- layer: RuvectorLayer::new / serde -------------------------------- */

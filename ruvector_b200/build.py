@@ -22,9 +22,26 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
+def source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive a snapshot)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(CSRC.glob("*")) + [PKG.parent / "include" / "ruvgnn.h"]
+    for f in files:
+        if f.is_file():
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source to objects (in parallel) and link the shared library."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    stamp = PKG / "libruvgnn.so.stamp"
+    want = source_hash()
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == want:
+        return LIB
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "ruvgnn.h"]
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
@@ -46,6 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if force or procs or _stale(LIB, objs):
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs)]
         subprocess.run(cmd, check=True)
+    stamp.write_text(want)
     return LIB
 
 

@@ -38,8 +38,12 @@ struct ruvgnn_ctx {
   float *x_stage = nullptr, *out_stage = nullptr;
   size_t x_stage_floats = 0, out_stage_floats = 0;
   int *d_flag = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float last_ms[5] = {0, 0, 0, 0, 0};
+  // timing ring: every RUVGNN_FWD_TIMING forward records 6 events into the next slot;
+  // ruvgnn_ctx_last_timing averages the slots recorded since the previous query.
+  static constexpr int kRing = 32;
+  cudaEvent_t ring[kRing][6] = {};
+  cudaEvent_t *ev = ring[0];
+  uint32_t ring_count = 0;
   bool timing_valid = false;
   // state of the last ruvgnn_layer_project
   uint64_t proj_rows = 0;
@@ -431,7 +435,8 @@ int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
     c->own_stream = true;
   }
   RUVGNN_CUDA_TRY(cudaMalloc(&c->d_flag, sizeof(int)));
-  for (auto &ev : c->ev) RUVGNN_CUDA_TRY(cudaEventCreate(&ev));
+  for (auto &slot : c->ring)
+    for (auto &ev : slot) RUVGNN_CUDA_TRY(cudaEventCreate(&ev));
   *out = c.release();
   return RUVGNN_OK;
 }
@@ -444,8 +449,9 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
   if (c->x_stage) cudaFree(c->x_stage);
   if (c->out_stage) cudaFree(c->out_stage);
   if (c->d_flag) cudaFree(c->d_flag);
-  for (auto &ev : c->ev)
-    if (ev) cudaEventDestroy(ev);
+  for (auto &slot : c->ring)
+    for (auto &ev : slot)
+      if (ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -460,16 +466,23 @@ uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
 
 int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms5) {
   if (!c || !ms5) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
-  if (!c->timing_valid) return fail(RUVGNN_ERR_INVALID_INPUT, "last forward was not timed");
+  if (c->ring_count == 0) return fail(RUVGNN_ERR_INVALID_INPUT, "no timed forward since last query");
   RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   // events: 0 start, 1 after h2d, 2 after project, 3 after gather, 4 after update, 5 after d2h
-  float h2d, proj, agg, upd, d2h;
-  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&h2d, c->ev[0], c->ev[1]));
-  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&proj, c->ev[1], c->ev[2]));
-  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, c->ev[2], c->ev[3]));
-  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&upd, c->ev[3], c->ev[4]));
-  RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, c->ev[4], c->ev[5]));
-  ms5[0] = proj; ms5[1] = agg; ms5[2] = upd; ms5[3] = h2d; ms5[4] = d2h;
+  const uint32_t nslots = c->ring_count < (uint32_t)ruvgnn_ctx::kRing ? c->ring_count : ruvgnn_ctx::kRing;
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (uint32_t sl = 0; sl < nslots; ++sl) {
+    cudaEvent_t *e = c->ring[sl];
+    float h2d, proj, agg, upd, d2h;
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&h2d, e[0], e[1]));
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&proj, e[1], e[2]));
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[2], e[3]));
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&upd, e[3], e[4]));
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, e[4], e[5]));
+    acc[0] += proj; acc[1] += agg; acc[2] += upd; acc[3] += h2d; acc[4] += d2h;
+  }
+  for (int i = 0; i < 5; ++i) ms5[i] = (float)(acc[i] / nslots);
+  c->ring_count = 0;
   return RUVGNN_OK;
 }
 
@@ -702,6 +715,8 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   if ((rc = ensure_ws(c, n, L->H))) return rc;
   if (timing) {
     c->timing_valid = true;
+    c->ev = c->ring[c->ring_count % ruvgnn_ctx::kRing];
+    ++c->ring_count;
     cudaEventRecord(c->ev[0], c->stream);
   }
   if (!dev_ptrs)
