@@ -211,8 +211,11 @@ def main():
     n_gpus = world
 
     x, g, w = build_inputs(a, rank, world)
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = rv.Context(local, stream)
+    # a dedicated non-default stream, made current, so torch's events and the library's
+    # kernels are on the same stream (handle 0 would make the library create its own)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    ctx = rv.Context(local, tstream.cuda_stream)
     layer = rv.RuvectorLayer(a.dim, a.dim, a.heads, 0.1, weights=w, ctx=ctx)
     mode = a.mode
     if mode < 0:
