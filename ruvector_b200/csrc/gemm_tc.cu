@@ -1,18 +1,608 @@
-// tcgen05 projection path -- placeholder translation unit until the kernel lands:
-// reports the path as unusable so ruvgnn_layer_set_mode() refuses tensor-core modes.
+// tcgen05 projection GEMMs for sm_100a (RUVGNN_MODE_FP32_TC / RUVGNN_MODE_TF32).
+//
+//   C[M x N] = [A1 | A2] * W^T + fused epilogue      (same contract as gemm_simt.cu)
+//
+// replaces the batched Linear::forward mat-vecs of crates/ruvector-gnn/src/layer.rs:37-41
+// (w_msg :392, q/k/v :135-137, out :159, w_agg :408, the six GRU linears :255-275).
+//
+// FP32 parity on tensor cores: tcgen05 has no FP32 MMA, kind::tf32 keeps 11 significant
+// bits of each input.  Every product is therefore error-compensated (3xTF32):
+//     a = a_hi + a_lo,  w = w_hi + w_lo   (hi = TF32-rounded, lo = exact remainder)
+//     a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi        (FP32 accumulate in TMEM)
+// dropping only a_lo*w_lo (<= 2^-22 relative).  Weights are split once at layer creation
+// and streamed by TMA; activation tiles are split by the producer warps on their way from
+// global memory into 128B-swizzled shared memory.
+//
+// CTA = 10 warps, persistent over output tiles (BLOCK_M = 128 rows x BLOCK_N <= 256 cols):
+//   warp 0      TMA producer: W_hi / W_lo k-blocks (32 floats = one 128B swizzle row)
+//   warp 1      MMA issuer (one elected lane), owns the TMEM allocation
+//   warps 2-5   A producers: LDG.128 -> hi/lo split -> STS into the swizzled A_hi / A_lo tiles
+//   warps 6-9   epilogue: tcgen05.ld the accumulator, bias / gates / GRU, global stores
+// Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <string.h>
+
+#include <vector>
+
 #include "gemm_tc.cuh"
 
 namespace ruvgnn {
+namespace {
 
-cudaError_t tc_weights_create(const float *const *, const uint32_t *, const uint32_t *,
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                          // floats per k-block = 128 bytes
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB per copy (hi or lo)
+constexpr int NUM_THREADS = 320;
+constexpr int MAX_STAGES = 4;
+
+struct TcParams {
+  GemmArgs g;
+  int block_n;
+  int stages;
+  int single_pass;
+  int num_m_tiles, num_n_tiles;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A protocol bug must fail fast, never hang the device: trap after 4 s of waiting.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    uint64_t t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout SWIZZLE_128B=2 [61,64).)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // LBO (ignored for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 bytes between 8-row groups
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ float sigmoid_ref(float x) {  // layer.rs:278-285
+  if (x > 0.f) return 1.0f / (1.0f + expf(-x));
+  const float ex = expf(x);
+  return ex / (1.0f + ex);
+}
+
+struct SmemLayout {
+  uint8_t *a_hi[MAX_STAGES], *a_lo[MAX_STAGES], *b_hi[MAX_STAGES], *b_lo[MAX_STAGES];
+  uint64_t *full_a, *full_b, *empty, *tmem_full, *tmem_empty;
+  uint32_t *tmem_ptr;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+               const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const GemmArgs &g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages = p.stages, BN = p.block_n;
+  const int b_tile_bytes = BN * BLOCK_K * 4;
+
+  // carve shared memory (tiles 1024-byte aligned for the 128B swizzle)
+  uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~(uintptr_t)1023);
+  SmemLayout sm;
+  for (int s = 0; s < stages; ++s) {
+    uint8_t *st = base + (size_t)s * (2 * A_TILE_BYTES + 2 * b_tile_bytes);
+    sm.a_hi[s] = st;
+    sm.a_lo[s] = st + A_TILE_BYTES;
+    sm.b_hi[s] = st + 2 * A_TILE_BYTES;
+    sm.b_lo[s] = st + 2 * A_TILE_BYTES + b_tile_bytes;
+  }
+  uint64_t *bars =
+      reinterpret_cast<uint64_t *>(base + (size_t)stages * (2 * A_TILE_BYTES + 2 * b_tile_bytes));
+  sm.full_a = bars;
+  sm.full_b = bars + MAX_STAGES;
+  sm.empty = bars + 2 * MAX_STAGES;
+  sm.tmem_full = bars + 3 * MAX_STAGES;
+  sm.tmem_empty = bars + 3 * MAX_STAGES + 2;
+  sm.tmem_ptr = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
+
+  const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                             : (2 * BN <= 256) ? 256 : 512;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_lo)) : "memory");
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&sm.full_a[s], 4);  // one arrive per A-producer warp
+      mbar_init(&sm.full_b[s], 1);  // TMA producer's arrive.expect_tx
+      mbar_init(&sm.empty[s], 1);   // tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.tmem_full[i], 1);   // tcgen05.commit
+      mbar_init(&sm.tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(sm.tmem_ptr, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
+
+  const int K = g.K1 + g.K2;
+  const int num_kb = K / BLOCK_K;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer: weight k-blocks =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&sm.empty[stage], phase ^ 1);
+          const uint32_t bytes = p.single_pass ? b_tile_bytes : 2 * b_tile_bytes;
+          mbar_arrive_expect_tx(&sm.full_b[stage], bytes);
+          tma_load_2d(sm.b_hi[stage], &map_hi, &sm.full_b[stage], kb * BLOCK_K, n0);
+          if (!p.single_pass)
+            tma_load_2d(sm.b_lo[stage], &map_lo, &sm.full_b[stage], kb * BLOCK_K, n0);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&sm.full_a[stage], phase);
+          mbar_wait(&sm.full_b[stage], phase);
+          tc_fence_after();
+          const uint64_t ah = make_desc_sw128(smem_u32(sm.a_hi[stage]));
+          const uint64_t al = make_desc_sw128(smem_u32(sm.a_lo[stage]));
+          const uint64_t bh = make_desc_sw128(smem_u32(sm.b_hi[stage]));
+          const uint64_t bl = make_desc_sw128(smem_u32(sm.b_lo[stage]));
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
+            const uint64_t off = (uint64_t)((kk * 32) >> 4);  // 8 tf32 = 32 bytes along K
+            const uint32_t first = (kb | kk) ? 1u : 0u;
+            if (p.single_pass) {
+              umma_tf32(d, ah + off, bh + off, idesc, first);
+            } else {
+              umma_tf32(d, al + off, bh + off, idesc, first);
+              umma_tf32(d, ah + off, bl + off, idesc, 1u);
+              umma_tf32(d, ah + off, bh + off, idesc, 1u);
+            }
+          }
+          umma_commit(&sm.empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&sm.tmem_full[acc]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== A producers: global -> (hi, lo) -> swizzled smem =====
+    const int t = threadIdx.x - 64;  // 0..127
+    const int chunk = t & 7;         // 16-byte chunk within the 128-byte row
+    const int rsub = t >> 3;         // 0..15
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t m0 = (int64_t)(tile / p.num_n_tiles) * BLOCK_M;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int k0 = kb * BLOCK_K;
+        const float *src;
+        int64_t ld;
+        if (k0 < g.K1) {
+          src = g.A1 + k0;
+          ld = g.lda1;
+        } else {
+          src = g.A2 + (k0 - g.K1);
+          ld = g.lda2;
+        }
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = m0 + i * 16 + rsub;
+          v[i] = row < g.M ? __ldg(reinterpret_cast<const float4 *>(src + row * ld) + chunk)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(&sm.empty[stage], phase ^ 1);
+        uint8_t *hi = sm.a_hi[stage], *lo = sm.a_lo[stage];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 16 + rsub;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          float4 h;
+          h.x = __uint_as_float((__float_as_uint(v[i].x) + 0x1000u) & 0xFFFFE000u);
+          h.y = __uint_as_float((__float_as_uint(v[i].y) + 0x1000u) & 0xFFFFE000u);
+          h.z = __uint_as_float((__float_as_uint(v[i].z) + 0x1000u) & 0xFFFFE000u);
+          h.w = __uint_as_float((__float_as_uint(v[i].w) + 0x1000u) & 0xFFFFE000u);
+          *reinterpret_cast<float4 *>(hi + off) = h;
+          if (!p.single_pass) {
+            float4 l;
+            l.x = v[i].x - h.x;
+            l.y = v[i].y - h.y;
+            l.z = v[i].z - h.z;
+            l.w = v[i].w - h.w;
+            *reinterpret_cast<float4 *>(lo + off) = l;
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.full_a[stage]);
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fused math -> global =====
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t row = (int64_t)(tile / p.num_n_tiles) * BLOCK_M + row_in_tile;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      mbar_wait(&sm.tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const bool live = row < g.M;
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        if (!live) continue;
+        const int col = n0 + c;
+        const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x;
+          v[4 * j + 1] += b.y;
+          v[4 * j + 2] += b.z;
+          v[4 * j + 3] += b.w;
+        }
+        if (EPI == EPI_BIAS) {
+          float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if (EPI == EPI_BIAS_ADD) {
+          const float4 *a = reinterpret_cast<const float4 *>(g.add + row * g.ldadd + col);
+          float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = a[j];
+            o[j] = make_float4(v[4 * j] + x.x, v[4 * j + 1] + x.y, v[4 * j + 2] + x.z,
+                               v[4 * j + 3] + x.w);
+          }
+        } else if (EPI == EPI_GATES) {
+          if (col < g.H) {
+            float4 *o = reinterpret_cast<float4 *>(g.z + row * g.ldz + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(sigmoid_ref(v[4 * j]), sigmoid_ref(v[4 * j + 1]),
+                                 sigmoid_ref(v[4 * j + 2]), sigmoid_ref(v[4 * j + 3]));
+          } else {
+            const int cc = col - g.H;
+            const float4 *m = reinterpret_cast<const float4 *>(g.m + row * g.ldm + cc);
+            float4 *o = reinterpret_cast<float4 *>(g.rh + row * g.ldrh + cc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = m[j];
+              o[j] = make_float4(sigmoid_ref(v[4 * j]) * x.x, sigmoid_ref(v[4 * j + 1]) * x.y,
+                                 sigmoid_ref(v[4 * j + 2]) * x.z, sigmoid_ref(v[4 * j + 3]) * x.w);
+            }
+          }
+        } else {  // EPI_GRU
+          const float4 *z4 = reinterpret_cast<const float4 *>(g.z + row * g.ldz + col);
+          const float4 *m4 = reinterpret_cast<const float4 *>(g.m + row * g.ldm + col);
+          float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 z = z4[j], m = m4[j];
+            float4 r;
+            r.x = ((1.0f - z.x) * m.x + z.x * tanhf(v[4 * j + 0])) * g.keep;
+            r.y = ((1.0f - z.y) * m.y + z.y * tanhf(v[4 * j + 1])) * g.keep;
+            r.z = ((1.0f - z.z) * m.z + z.z * tanhf(v[4 * j + 2])) * g.keep;
+            r.w = ((1.0f - z.w) * m.w + z.w * tanhf(v[4 * j + 3])) * g.keep;
+            o[j] = r;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int pick_block_n(uint32_t n) {
+  for (int bn = 256; bn >= 32; bn -= 32)  // epilogue walks 32-column chunks
+    if (n % bn == 0) return bn;
+  return 0;
+}
+
+struct TcMaps {
+  CUtensorMap hi[TC_W_COUNT], lo[TC_W_COUNT];
+  int block_n[TC_W_COUNT];
+};
+
+template <int EPI>
+cudaError_t launch_epi(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int grid,
+                       size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gemm_tc_kernel<EPI><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
+                              const uint32_t rows[TC_W_COUNT], const uint32_t cols[TC_W_COUNT],
                               TcWeights *out) {
   out->usable = false;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return cudaSuccess;  // driver too old for TMA descriptors: path stays unusable
+  size_t total = 0;
+  for (int i = 0; i < TC_W_COUNT; ++i) {
+    if (cols[i] % BLOCK_K != 0 || pick_block_n(rows[i]) == 0) return cudaSuccess;
+    total += 2 * (size_t)rows[i] * cols[i];
+  }
+  // the K-concatenated GEMMs switch A source at column H: H itself must be a k-block multiple
+  if (rows[TC_W_O] % BLOCK_K != 0) return cudaSuccess;
+  std::vector<float> blob(total);
+  size_t off = 0;
+  size_t offs_hi[TC_W_COUNT], offs_lo[TC_W_COUNT];
+  for (int i = 0; i < TC_W_COUNT; ++i) {
+    const size_t n = (size_t)rows[i] * cols[i];
+    offs_hi[i] = off;
+    offs_lo[i] = off + n;
+    for (size_t j = 0; j < n; ++j) {
+      const float w = host_mats[i][j];
+      uint32_t b;
+      memcpy(&b, &w, 4);
+      b = (b + 0x1000u) & 0xFFFFE000u;  // round to TF32 (10 explicit mantissa bits)
+      float h;
+      memcpy(&h, &b, 4);
+      blob[off + j] = h;
+      blob[off + n + j] = w - h;  // exact in FP32
+    }
+    off += 2 * n;
+  }
+  cudaError_t e = cudaMalloc(&out->blob, total * sizeof(float));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(out->blob, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  TcMaps *maps = new TcMaps();
+  for (int i = 0; i < TC_W_COUNT; ++i) {
+    out->hi[i] = out->blob + offs_hi[i];
+    out->lo[i] = out->blob + offs_lo[i];
+    out->rows[i] = rows[i];
+    out->cols[i] = cols[i];
+    maps->block_n[i] = pick_block_n(rows[i]);
+    const cuuint64_t dims[2] = {cols[i], rows[i]};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols[i] * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)maps->block_n[i]};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int part = 0; part < 2; ++part) {
+      CUresult r = encode(part ? &maps->lo[i] : &maps->hi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          part ? out->lo[i] : out->hi[i], dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        delete maps;
+        cudaFree(out->blob);
+        out->blob = nullptr;
+        return cudaErrorInvalidValue;
+      }
+    }
+  }
+  out->tmaps = maps;
+  out->usable = true;
   return cudaSuccess;
 }
-void tc_weights_destroy(TcWeights *) {}
-cudaError_t launch_gemm_tc(const GemmArgs &, EpiKind, const TcWeights &, int, bool, int,
-                           cudaStream_t, uint64_t *) {
-  return cudaErrorNotSupported;
+
+void tc_weights_destroy(TcWeights *w) {
+  if (w->blob) cudaFree(w->blob);
+  w->blob = nullptr;
+  delete static_cast<TcMaps *>(w->tmaps);
+  w->tmaps = nullptr;
+  w->usable = false;
+}
+
+cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, int which,
+                           bool single_pass, int sm_count, cudaStream_t s, uint64_t *launches) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  const TcMaps *maps = static_cast<const TcMaps *>(w.tmaps);
+  if (!w.usable || !maps) return cudaErrorNotSupported;
+  if ((uint32_t)g.N != w.rows[which] || (uint32_t)(g.K1 + g.K2) != w.cols[which] ||
+      g.K1 % BLOCK_K != 0 || g.K2 % BLOCK_K != 0)
+    return cudaErrorInvalidValue;
+  TcParams p;
+  p.g = g;
+  p.block_n = maps->block_n[which];
+  p.single_pass = single_pass ? 1 : 0;
+  p.num_m_tiles = (int)((g.M + BLOCK_M - 1) / BLOCK_M);
+  p.num_n_tiles = g.N / p.block_n;
+  const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.block_n * BLOCK_K * 4;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return cudaErrorInvalidValue;
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
+  const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+  if (launches) ++*launches;
+  switch (epi) {
+    case EPI_BIAS: return launch_epi<EPI_BIAS>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+    case EPI_BIAS_ADD:
+      return launch_epi<EPI_BIAS_ADD>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+    case EPI_GATES:
+      return launch_epi<EPI_GATES>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+    case EPI_GRU: return launch_epi<EPI_GRU>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace ruvgnn
