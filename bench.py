@@ -143,7 +143,9 @@ def build_inputs(a, rank, world):
     from ruvector_b200 import synth
 
     x = synth.make_features(a.nodes, a.dim, seed=0x5EED + rank)
-    g = synth.hnsw_like_graph(a.nodes, a.m, seed=0xBEEF + rank, locality=a.locality)
+    # rank r owns rows [r*nodes, (r+1)*nodes) of a (world*nodes)-node graph; columns are global
+    g = synth.hnsw_like_graph(a.nodes, a.m, seed=0xBEEF + rank, locality=a.locality,
+                              n_total=a.nodes * world, row_offset=rank * a.nodes)
     w = synth.make_weights(a.dim, a.dim)
     return x, g, w
 
@@ -235,7 +237,10 @@ def main():
         from ruvector_b200 import dist as rvdist
 
         part = rvdist.Partition.build(g, rank, world, a.nodes, ctx)
-        step_fn = lambda xd, od, timing=False: part.forward(layer, xd, od, timing=timing)
+
+        def step_fn(xd, od, timing=False):
+            ctx.set_timing(timing)
+            part.forward(layer, xd, od)
         dg = part.graph
     else:
         dg = g.to_device(ctx)
@@ -272,11 +277,14 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
     # per-stage device times of the last timed step (events on the launching stream)
+    exchange_ms = None
     try:
         t = ctx.last_timing()
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
+        exchange_ms = t["exchange_ms"]
     except rv.GnnError:
         pass
+    ctx.set_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tmax = torch.tensor([ms], device="cuda")
@@ -354,7 +362,10 @@ def main():
         "edges_per_sec": E_total / (ms_per_step * 1e-3),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
     }
-    if not a.no_cpu_baseline:
+    if world > 1:
+        line["halo"] = {"rows_received_rank0": part.plan.n_halo, "rows_sent_rank0": int(part.plan.send_idx.size),
+                        "bytes_exchanged_rank0": int(part.bytes_exchanged), "exchange_ms_rank0": exchange_ms}
+    if not a.no_cpu_baseline and world == 1:
         cb, _, _ = cpu_baseline(a, layer, x, g, a.cpu_seconds)
         line["cpu_baseline"] = cb
     print(json.dumps(line))

@@ -58,10 +58,12 @@ int32_t ruvgnn_sync(ruvgnn_ctx *ctx);
 void *ruvgnn_ctx_stream(ruvgnn_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *ctx);
-/* Device milliseconds per stage (0 project, 1 aggregate, 2 update, 3 h2d, 4 d2h),
- * averaged over the RUVGNN_FWD_TIMING forwards (up to 32) since the previous query;
- * CUDA events on the launching stream.  Synchronises the stream. */
-int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *ctx, float *ms5);
+/* Device milliseconds per stage (0 project, 1 aggregate, 2 update, 3 h2d, 4 d2h,
+ * 5 halo exchange wait), averaged over the timed forwards (up to 32) since the
+ * previous query; CUDA events on the launching stream.  Synchronises the stream. */
+int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *ctx, float *ms6);
+/* Also time the phased entries (ruvgnn_layer_project / ruvgnn_layer_aggregate_update). */
+int32_t ruvgnn_ctx_set_timing(ruvgnn_ctx *ctx, int32_t on);
 
 /* ---- layer: RuvectorLayer::new / serde -------------------------------- */
 

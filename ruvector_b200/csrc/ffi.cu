@@ -38,10 +38,13 @@ struct ruvgnn_ctx {
   float *x_stage = nullptr, *out_stage = nullptr;
   size_t x_stage_floats = 0, out_stage_floats = 0;
   int *d_flag = nullptr;
-  // timing ring: every RUVGNN_FWD_TIMING forward records 6 events into the next slot;
+  // timing ring: every timed forward records 7 events into the next slot;
   // ruvgnn_ctx_last_timing averages the slots recorded since the previous query.
+  // events: 0 start, 1 after h2d, 2 after project, 6 aggregate start (after the halo
+  // exchange in the partitioned path), 3 after gather, 4 after update, 5 after d2h
   static constexpr int kRing = 32;
-  cudaEvent_t ring[kRing][6] = {};
+  cudaEvent_t ring[kRing][7] = {};
+  bool timing_on = false;  // ruvgnn_ctx_set_timing: also time project / aggregate_update
   cudaEvent_t *ev = ring[0];
   uint32_t ring_count = 0;
   bool timing_valid = false;
@@ -226,6 +229,7 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
   ga.H = H;
   ga.heads = L->heads;
   ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+  if (c->timing_valid) cudaEventRecord(c->ev[6], c->stream);
   RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
   if (c->timing_valid) cudaEventRecord(c->ev[3], c->stream);
 
@@ -464,24 +468,30 @@ int32_t ruvgnn_sync(ruvgnn_ctx *c) {
 void *ruvgnn_ctx_stream(ruvgnn_ctx *c) { return c ? c->stream : nullptr; }
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
 
-int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms5) {
-  if (!c || !ms5) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+int32_t ruvgnn_ctx_set_timing(ruvgnn_ctx *c, int32_t on) {
+  if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
+  c->timing_on = on != 0;
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms6) {
+  if (!c || !ms6) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (c->ring_count == 0) return fail(RUVGNN_ERR_INVALID_INPUT, "no timed forward since last query");
   RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  // events: 0 start, 1 after h2d, 2 after project, 3 after gather, 4 after update, 5 after d2h
   const uint32_t nslots = c->ring_count < (uint32_t)ruvgnn_ctx::kRing ? c->ring_count : ruvgnn_ctx::kRing;
-  double acc[5] = {0, 0, 0, 0, 0};
+  double acc[6] = {0, 0, 0, 0, 0, 0};
   for (uint32_t sl = 0; sl < nslots; ++sl) {
     cudaEvent_t *e = c->ring[sl];
-    float h2d, proj, agg, upd, d2h;
+    float h2d, proj, xchg, agg, upd, d2h;
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&h2d, e[0], e[1]));
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&proj, e[1], e[2]));
-    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[2], e[3]));
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&xchg, e[2], e[6]));
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[6], e[3]));
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&upd, e[3], e[4]));
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, e[4], e[5]));
-    acc[0] += proj; acc[1] += agg; acc[2] += upd; acc[3] += h2d; acc[4] += d2h;
+    acc[0] += proj; acc[1] += agg; acc[2] += upd; acc[3] += h2d; acc[4] += d2h; acc[5] += xchg;
   }
-  for (int i = 0; i < 5; ++i) ms5[i] = (float)(acc[i] / nslots);
+  for (int i = 0; i < 6; ++i) ms6[i] = (float)(acc[i] / nslots);
   c->ring_count = 0;
   return RUVGNN_OK;
 }
@@ -781,8 +791,16 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   if (!c || !L || !x_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
-  c->timing_valid = false;
-  return do_project(c, L, n_local, x_dev);
+  c->timing_valid = c->timing_on;
+  if (c->timing_on) {
+    c->ev = c->ring[c->ring_count % ruvgnn_ctx::kRing];
+    ++c->ring_count;
+    cudaEventRecord(c->ev[0], c->stream);
+    cudaEventRecord(c->ev[1], c->stream);
+  }
+  int32_t rc = do_project(c, L, n_local, x_dev);
+  if (c->timing_on) cudaEventRecord(c->ev[2], c->stream);
+  return rc;
 }
 
 int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *idx_dev,
@@ -812,8 +830,13 @@ int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, cons
     return fail(RUVGNN_ERR_INVALID_INPUT, "row range out of bounds");
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
-  c->timing_valid = false;
-  return do_aggregate_update(c, L, G, halo_dev, row_begin, row_end, out_dev);
+  c->timing_valid = c->timing_on;
+  int32_t rc = do_aggregate_update(c, L, G, halo_dev, row_begin, row_end, out_dev);
+  if (c->timing_on) {
+    cudaEventRecord(c->ev[4], c->stream);
+    cudaEventRecord(c->ev[5], c->stream);
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -1,0 +1,178 @@
+"""Range-partitioned multi-GPU forward with halo exchange.
+
+One process per GPU (``torch.distributed``).  Nodes are split into contiguous ranges;
+rank p owns rows ``[bounds[p], bounds[p+1])`` of X and of the CSR, projects its own rows,
+and needs the projected K|V|M rows of every *remote* neighbour its rows reference.  Those
+are de-duplicated per peer once per graph (:class:`HaloPlan`, pure host logic) and moved
+once per layer with a single all-to-all-v over NCCL/NVLink into a halo buffer the
+gather kernel addresses as rows ``n_local + slot``.  Neighbour order inside every row is
+preserved (indices are remapped, never reordered), so a partitioned run performs exactly
+the per-row arithmetic of the single-GPU run.
+
+The reference has no multi-device path at all; weights (< 30 MB) are
+replicated, exactly like its ``Clone``-able layer (gnn_cache.rs:183-188).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .graph import CsrGraph
+
+
+def even_bounds(n_total: int, world: int) -> np.ndarray:
+    """Contiguous ranges [p*N/P, (p+1)*N/P)."""
+    return np.array([(n_total * p) // world for p in range(world + 1)], dtype=np.int64)
+
+
+@dataclass
+class HaloPlan:
+    """Host-side exchange plan of one rank.
+
+    ``graph``       local CSR with remapped columns: < n_local own row, >= n_local halo slot
+    ``need_ids``    global ids of the halo rows, slot order (sorted => grouped by owner)
+    ``recv_counts`` rows received from each peer (sum == n_halo)
+    ``req_local``   per peer: the peer-local row indices this rank asks that peer for
+    ``send_idx``    (after :meth:`set_requests`) own-local rows to send, concatenated by peer
+    ``send_counts`` rows sent to each peer
+    """
+
+    rank: int
+    world: int
+    bounds: np.ndarray
+    graph: CsrGraph
+    need_ids: np.ndarray
+    recv_counts: np.ndarray
+    req_local: List[np.ndarray]
+    send_idx: Optional[np.ndarray] = None
+    send_counts: Optional[np.ndarray] = None
+
+    @property
+    def n_local(self) -> int:
+        return int(self.bounds[self.rank + 1] - self.bounds[self.rank])
+
+    @property
+    def n_halo(self) -> int:
+        return int(self.need_ids.size)
+
+    @classmethod
+    def build(cls, local_rows: CsrGraph, rank: int, bounds: Sequence[int]) -> "HaloPlan":
+        """``local_rows``: this rank's CSR rows with GLOBAL column ids."""
+        bounds = np.asarray(bounds, dtype=np.int64)
+        world = bounds.size - 1
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        if local_rows.n_nodes != hi - lo:
+            raise ValueError("local_rows must hold exactly this rank's rows")
+        col = local_rows.col_idx.astype(np.int64)
+        if col.size and (col.min() < 0 or col.max() >= bounds[-1]):
+            raise ValueError("column id outside the global node range")
+        remote = (col < lo) | (col >= hi)
+        need = np.unique(col[remote])  # sorted: grouped by owner, ascending id inside
+        new_col = np.where(remote, 0, col - lo)
+        if need.size:
+            new_col[remote] = (hi - lo) + np.searchsorted(need, col[remote])
+        if (hi - lo) + need.size > 0xFFFFFFFF:
+            raise ValueError("local + halo rows exceed u32 column indices")
+        owner_edges = np.searchsorted(need, bounds)  # need[owner_edges[p]:owner_edges[p+1]] live on p
+        recv_counts = np.diff(owner_edges).astype(np.int64)
+        req_local = [(need[owner_edges[p]:owner_edges[p + 1]] - bounds[p]).astype(np.int64) for p in range(world)]
+        g = CsrGraph(local_rows.row_ptr.copy(), new_col.astype(np.uint32), local_rows.edge_w.copy())
+        return cls(rank, world, bounds, g, need, recv_counts, req_local)
+
+    def set_requests(self, requests_from_peers: Sequence[np.ndarray]):
+        """``requests_from_peers[p]`` = own-local row indices peer p asked for."""
+        n = self.n_local
+        for p, r in enumerate(requests_from_peers):
+            if r.size and (r.min() < 0 or r.max() >= n):
+                raise ValueError(f"peer {p} requested a row this rank does not own")
+        self.send_counts = np.array([r.size for r in requests_from_peers], dtype=np.int64)
+        self.send_idx = (np.concatenate(requests_from_peers) if requests_from_peers else np.zeros(0)).astype(np.uint32)
+        return self
+
+
+def exchange_requests(plan: HaloPlan, group=None) -> HaloPlan:
+    """All-to-all of the request lists (once per graph).  Works on gloo (CPU) and nccl."""
+    import torch
+    import torch.distributed as dist
+
+    if plan.world == 1:
+        return plan.set_requests([np.zeros(0, dtype=np.int64)])
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    out_counts = torch.tensor(plan.recv_counts, dtype=torch.int64, device=dev)  # what I ask of each peer
+    in_counts = torch.empty_like(out_counts)
+    dist.all_to_all_single(in_counts, out_counts, group=group)
+    send = torch.from_numpy(np.concatenate(plan.req_local).astype(np.int64)).to(dev)
+    recv = torch.empty(int(in_counts.sum().item()), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, in_counts.tolist(), out_counts.tolist(), group=group)
+    recv = recv.cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(in_counts.cpu().numpy())])
+    return plan.set_requests([recv[offs[p]:offs[p + 1]] for p in range(plan.world)])
+
+
+def exchange_rows(plan: HaloPlan, send_rows, group=None):
+    """Per-layer all-to-all-v: ``send_rows`` [n_send, W] (rows ``plan.send_idx`` of the projected
+    block, already packed) -> halo [n_halo, W] in slot order."""
+    import torch
+    import torch.distributed as dist
+
+    halo = torch.empty((plan.n_halo, send_rows.shape[1]), dtype=send_rows.dtype, device=send_rows.device)
+    if plan.world == 1:
+        return halo
+    dist.all_to_all_single(halo, send_rows, plan.recv_counts.tolist(), plan.send_counts.tolist(), group=group)
+    return halo
+
+
+class Partition:
+    """Device-side state of one rank: plan, device CSR, send indices, buffers."""
+
+    def __init__(self, plan: HaloPlan, ctx):
+        import torch
+
+        self.plan, self.ctx = plan, ctx
+        self.graph = plan.graph.to_device(ctx, n_cols=plan.n_local + plan.n_halo)
+        self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
+        self._send = self._halo = self._x = self._out = None
+        self.bytes_exchanged = 0
+
+    @classmethod
+    def build(cls, local_rows: CsrGraph, rank: int, world: int, n_per_rank: int, ctx) -> "Partition":
+        plan = HaloPlan.build(local_rows, rank, even_bounds(n_per_rank * world, world))
+        return cls(exchange_requests(plan), ctx)
+
+    def forward(self, layer, x_dev, out_dev, timing: bool = False):
+        """project -> pack -> all-to-all-v (NCCL) -> gather/aggregate + update.  Enqueue only."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        lib, plan, H = _lib.load(), self.plan, layer.hidden_dim
+        h = layer._device_layer()
+        _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, plan.n_local, C.c_void_p(x_dev.data_ptr())))
+        n_send = int(self.send_idx.numel())
+        if self._send is None or self._send.shape != (n_send, 3 * H):
+            self._send = torch.empty((n_send, 3 * H), dtype=torch.float32, device=x_dev.device)
+        if n_send:
+            _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
+                                            C.c_void_p(self._send.data_ptr())))
+        self._halo = exchange_rows(plan, self._send)
+        self.bytes_exchanged = (n_send + plan.n_halo) * 3 * H * 4
+        halo_ptr = self._halo.data_ptr() if plan.n_halo else None
+        _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr), 0,
+                                                     plan.n_local, C.c_void_p(out_dev.data_ptr())))
+
+    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray):
+        """Host buffers in, host buffers out (H2D / D2H inside): the e2e leg of bench.py."""
+        import torch
+
+        xt, ot = torch.from_numpy(x_np), torch.from_numpy(out_np)
+        if self._x is None or self._x.shape != xt.shape:
+            self._x = torch.empty(xt.shape, dtype=torch.float32, device="cuda")
+            self._out = torch.empty(ot.shape, dtype=torch.float32, device="cuda")
+        self._x.copy_(xt, non_blocking=True)
+        self.forward(layer, self._x, self._out)
+        ot.copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()

@@ -46,9 +46,12 @@ class Context:
         return int(self._lib.ruvgnn_ctx_launch_count(self.handle))
 
     def last_timing(self) -> dict:
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 6)()
         _lib.check(self._lib.ruvgnn_ctx_last_timing(self.handle, ms))
-        return dict(zip(("project_ms", "aggregate_ms", "update_ms", "h2d_ms", "d2h_ms"), map(float, ms)))
+        return dict(zip(("project_ms", "aggregate_ms", "update_ms", "h2d_ms", "d2h_ms", "exchange_ms"), map(float, ms)))
+
+    def set_timing(self, on: bool):
+        _lib.check(self._lib.ruvgnn_ctx_set_timing(self.handle, 1 if on else 0))
 
     def close(self):
         if getattr(self, "handle", None):

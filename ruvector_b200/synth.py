@@ -43,7 +43,8 @@ def make_weights(input_dim: int, hidden_dim: int, seed: int = 0xC0FFEE, trivial:
 
 
 def hnsw_like_graph(n: int, m: int, seed: int = 0xBEEF, locality: float = 0.0, window: int = 4096,
-                    iso_frac: float = 0.01, level: int = 0) -> CsrGraph:
+                    iso_frac: float = 0.01, level: int = 0, n_total: int | None = None,
+                    row_offset: int = 0) -> CsrGraph:
     """HNSW-shaped random adjacency (no self loops, no duplicate neighbour in a row).
 
     Level 0: out-degree ~ U{M..2M} (cap 2M, hnsw.rs:1169); level l>=1: U{M/2..M} over the
@@ -51,10 +52,14 @@ def hnsw_like_graph(n: int, m: int, seed: int = 0xBEEF, locality: float = 0.0, w
     from a +-``window`` id range (0 = insertion-order worst case).  ``iso_frac`` of the
     nodes get no neighbours (layer.rs:385-389 path).  ``edge_w`` is ascending U(0,1) per
     row, like HNSW's distance-sorted lists (hnsw.rs:1186).
+
+    ``n_total`` / ``row_offset``: generate only the rows ``[row_offset, row_offset + n)`` of an
+    ``n_total``-node graph, with GLOBAL column ids (one partition of a multi-GPU run).
     """
+    nt = n if n_total is None else n_total
     g = _rng(seed, level)
     lo, hi = (m, 2 * m) if level == 0 else (max(m // 2, 1), m)
-    hi = min(hi, max(n - 1, 0))
+    hi = min(hi, max(nt - 1, 0))
     lo = min(lo, hi)
     deg = g.integers(lo, hi + 1, size=n, dtype=np.int64) if hi > 0 else np.zeros(n, dtype=np.int64)
     if level > 0:
@@ -67,18 +72,18 @@ def hnsw_like_graph(n: int, m: int, seed: int = 0xBEEF, locality: float = 0.0, w
     np.cumsum(deg, out=row_ptr[1:].view(np.int64))
     if width == 0:
         return CsrGraph(row_ptr, np.zeros(0, np.uint32), np.zeros(0, F32))
-    rows = np.arange(n, dtype=np.int64)[:, None]
+    rows = row_offset + np.arange(n, dtype=np.int64)[:, None]
 
     def draw(shape_rows):
         r = shape_rows.shape[0]
-        far = g.integers(0, n - 1, size=(r, width), dtype=np.int64)
+        far = g.integers(0, nt - 1, size=(r, width), dtype=np.int64)
         far += far >= shape_rows  # skip self
         if locality <= 0:
             return far
-        w = min(window, max((n - 1) // 2, 1))
+        w = min(window, max((nt - 1) // 2, 1))
         off = g.integers(1, w + 1, size=(r, width), dtype=np.int64) * g.choice(np.array([-1, 1]), size=(r, width))
-        near = (shape_rows + off) % n
-        near = np.where(near == shape_rows, (near + 1) % n, near)
+        near = (shape_rows + off) % nt
+        near = np.where(near == shape_rows, (near + 1) % nt, near)
         return np.where(g.random((r, width)) < locality, near, far)
 
     cols = draw(rows)
