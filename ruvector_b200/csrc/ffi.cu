@@ -45,6 +45,10 @@ struct ruvgnn_ctx {
   static constexpr int kRing = 32;
   cudaEvent_t ring[kRing][7] = {};
   bool timing_on = false;  // ruvgnn_ctx_set_timing: also time project / aggregate_update
+  // host-buffer forward: copy streams + per-block events for the H2D | compute | D2H pipeline
+  static constexpr int kMaxBlocks = 16;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kMaxBlocks] = {}, ev_out[kMaxBlocks] = {}, ev_start = nullptr, ev_done = nullptr;
   cudaEvent_t *ev = ring[0];
   uint32_t ring_count = 0;
   bool timing_valid = false;
@@ -175,42 +179,49 @@ int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKin
 
 // Phase A (K-proj): M = X W_msg^T + b (layer.rs:392-396, once per node instead of once
 // per edge), then Q|K|V = M [W_q;W_k;W_v]^T + b (:135-137).
-int32_t do_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev) {
+// Projects rows [rb, re) of an n-row partition (x_dev is the base of all n rows).
+int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev,
+                        uint64_t rb, uint64_t re) {
   const uint32_t H = L->H, D = L->D;
   int32_t rc = ensure_ws(c, n, H);
   if (rc) return rc;
+  if (re <= rb) return RUVGNN_OK;
   Ws w = carve(c, n, H);
   GemmArgs g;
-  g.M = (int64_t)n;
+  g.M = (int64_t)(re - rb);
   g.N = (int32_t)H;
   g.K1 = (int32_t)D;
-  g.A1 = x_dev;
+  g.A1 = x_dev + rb * D;
   g.lda1 = D;
   g.W = L->Wmsg;
   g.bias = L->bmsg;
-  g.out = w.P + 3 * H;
+  g.out = w.P + rb * w.ldp + 3 * H;
   g.ldo = w.ldp;
   if ((rc = run_gemm(c, L, g, EPI_BIAS, TC_W_MSG))) return rc;
   GemmArgs q;
-  q.M = (int64_t)n;
+  q.M = (int64_t)(re - rb);
   q.N = (int32_t)(3 * H);
   q.K1 = (int32_t)H;
-  q.A1 = w.P + 3 * H;
+  q.A1 = w.P + rb * w.ldp + 3 * H;
   q.lda1 = w.ldp;
   q.W = L->Wqkv;
   q.bias = L->bqkv;
-  q.out = w.P;
+  q.out = w.P + rb * w.ldp;
   q.ldo = w.ldp;
   if ((rc = run_gemm(c, L, q, EPI_BIAS, TC_W_QKV))) return rc;
   c->proj_rows = n;
   c->proj_H = H;
   return RUVGNN_OK;
 }
+int32_t do_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev) {
+  return do_project_rows(c, L, n, x_dev, 0, n);
+}
 
 // Phase B: K-agg over rows [rb,re), then K-upd (out-proj + combine + W_agg, GRU,
 // dropout scale, LayerNorm; layer.rs:156-159,407-417).
 int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
-                            const float *halo, uint64_t rb, uint64_t re, float *out_dev) {
+                            const float *halo, uint64_t rb, uint64_t re, float *out_dev,
+                            bool stage_events = true) {
   const uint32_t H = L->H;
   const uint64_t n = c->proj_rows;
   if (re <= rb) return RUVGNN_OK;
@@ -229,9 +240,9 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
   ga.H = H;
   ga.heads = L->heads;
   ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
-  if (c->timing_valid) cudaEventRecord(c->ev[6], c->stream);
+  if (c->timing_valid && stage_events) cudaEventRecord(c->ev[6], c->stream);
   RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
-  if (c->timing_valid) cudaEventRecord(c->ev[3], c->stream);
+  if (c->timing_valid && stage_events) cudaEventRecord(c->ev[3], c->stream);
 
   const int64_t rows = (int64_t)(re - rb);
   const float *m = w.P + rb * w.ldp + 3 * H;
@@ -441,6 +452,12 @@ int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
   RUVGNN_CUDA_TRY(cudaMalloc(&c->d_flag, sizeof(int)));
   for (auto &slot : c->ring)
     for (auto &ev : slot) RUVGNN_CUDA_TRY(cudaEventCreate(&ev));
+  RUVGNN_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  RUVGNN_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (auto &ev : c->ev_in) RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->ev_out) RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   *out = c.release();
   return RUVGNN_OK;
 }
@@ -456,6 +473,14 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
   for (auto &slot : c->ring)
     for (auto &ev : slot)
       if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_in)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_out)
+    if (ev) cudaEventDestroy(ev);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -729,18 +754,62 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
     ++c->ring_count;
     cudaEventRecord(c->ev[0], c->stream);
   }
-  if (!dev_ptrs)
-    RUVGNN_CUDA_TRY(cudaMemcpyAsync(c->x_stage, x, (size_t)n * L->D * sizeof(float),
-                                    cudaMemcpyHostToDevice, c->stream));
-  if (timing) cudaEventRecord(c->ev[1], c->stream);
-  if ((rc = do_project(c, L, n, x_dev))) return rc;
-  if (timing) cudaEventRecord(c->ev[2], c->stream);
-  if ((rc = do_aggregate_update(c, L, G, nullptr, 0, n, out_dev))) return rc;
-  if (timing) cudaEventRecord(c->ev[4], c->stream);
-  if (!dev_ptrs)
-    RUVGNN_CUDA_TRY(cudaMemcpyAsync(out, c->out_stage, (size_t)n * L->H * sizeof(float),
-                                    cudaMemcpyDeviceToHost, c->stream));
-  if (timing) cudaEventRecord(c->ev[5], c->stream);
+  if (dev_ptrs) {
+    if (timing) cudaEventRecord(c->ev[1], c->stream);
+    if ((rc = do_project(c, L, n, x_dev))) return rc;
+    if (timing) cudaEventRecord(c->ev[2], c->stream);
+    if ((rc = do_aggregate_update(c, L, G, nullptr, 0, n, out_dev))) return rc;
+    if (timing) {
+      cudaEventRecord(c->ev[4], c->stream);
+      cudaEventRecord(c->ev[5], c->stream);
+    }
+  } else {
+    // Host buffers: row-block pipeline.  H2D of block b+1 overlaps the projection of block b
+    // (copy stream s_in); every row must be projected before any gather (neighbours are
+    // arbitrary rows); then gather + update of block b overlaps the D2H of block b-1 (s_out).
+    const uint64_t target = 131072;
+    uint64_t nb = (n + target - 1) / target;
+    if (nb > (uint64_t)ruvgnn_ctx::kMaxBlocks) nb = ruvgnn_ctx::kMaxBlocks;
+    if (nb < 1) nb = 1;
+    const uint64_t per = ((n + nb - 1) / nb + 127) / 128 * 128;
+    RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_start, c->stream));
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_start, 0));
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_start, 0));
+    uint64_t used = 0;
+    for (uint64_t b = 0; b < nb; ++b) {
+      const uint64_t rb = b * per, re = rb + per < n ? rb + per : n;
+      if (rb >= n) break;
+      ++used;
+      RUVGNN_CUDA_TRY(cudaMemcpyAsync(c->x_stage + rb * L->D, x + rb * L->D,
+                                      (re - rb) * L->D * sizeof(float), cudaMemcpyHostToDevice,
+                                      c->s_in));
+      RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_in[b], c->s_in));
+    }
+    for (uint64_t b = 0; b < used; ++b) {
+      const uint64_t rb = b * per, re = rb + per < n ? rb + per : n;
+      RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+      if (timing && b == used - 1) cudaEventRecord(c->ev[1], c->stream);
+      if ((rc = do_project_rows(c, L, n, x_dev, rb, re))) return rc;
+    }
+    if (timing) {
+      cudaEventRecord(c->ev[2], c->stream);
+      cudaEventRecord(c->ev[6], c->stream);
+      cudaEventRecord(c->ev[3], c->stream);
+    }
+    for (uint64_t b = 0; b < used; ++b) {
+      const uint64_t rb = b * per, re = rb + per < n ? rb + per : n;
+      if ((rc = do_aggregate_update(c, L, G, nullptr, rb, re, out_dev, false))) return rc;
+      RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_out[b], c->stream));
+      RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_out[b], 0));
+      RUVGNN_CUDA_TRY(cudaMemcpyAsync(out + rb * L->H, c->out_stage + rb * L->H,
+                                      (re - rb) * L->H * sizeof(float), cudaMemcpyDeviceToHost,
+                                      c->s_out));
+    }
+    if (timing) cudaEventRecord(c->ev[4], c->stream);
+    RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_done, c->s_out));
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+    if (timing) cudaEventRecord(c->ev[5], c->stream);
+  }
   if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RUVGNN_OK;
 }
