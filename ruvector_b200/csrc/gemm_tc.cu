@@ -21,6 +21,7 @@
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -31,10 +32,11 @@ namespace ruvgnn {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;                          // floats per k-block = 128 bytes
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB per copy (hi or lo)
+// BK = floats per k-block: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B).
+// The smaller k-block halves the stage size, so twice as many stages fit in shared memory
+// and more operand bytes are in flight per SM.
 constexpr int NUM_THREADS = 320;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 
 struct TcParams {
   GemmArgs g;
@@ -149,17 +151,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// K-major swizzled operand tile: rows of BK*4 bytes (128 or 64), 8-row groups contiguous.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-//  version=1 [46,48), layout SWIZZLE_128B=2 [61,64).)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+//  version=1 [46,48), layout [61,64): SWIZZLE_128B=2, SWIZZLE_64B=4.)
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;            // LBO (ignored for swizzled K-major), canonical value 1
-  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 bytes between 8-row groups
-  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  d |= (uint64_t)1 << 16;                   // LBO (ignored for swizzled K-major), canonical 1
+  d |= (uint64_t)((8 * BK * 4) >> 4) << 32;  // SBO = bytes between 8-row groups
+  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+  d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;  // SWIZZLE_128B / SWIZZLE_64B
   return d;
+}
+// Byte offset of 16-byte chunk `chunk` of row `r` inside a swizzled tile (what TMA produces
+// for CU_TENSOR_MAP_SWIZZLE_128B / _64B: address bits [4,7) ^= [7,10), resp. [4,6) ^= [7,9)).
+template <int BK>
+__device__ __forceinline__ uint32_t swz_off(int r, int chunk) {
+  if (BK == 32) return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+  return (uint32_t)r * 64u + (uint32_t)((chunk ^ ((r >> 1) & 3)) << 4);
 }
 // cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29).
@@ -180,13 +190,15 @@ struct SmemLayout {
   uint32_t *tmem_ptr;
 };
 
-template <int EPI>
+template <int EPI, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmArgs &g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int BLOCK_K = BK;
+  constexpr int A_TILE_BYTES = BLOCK_M * BK * 4;
   const int stages = p.stages, BN = p.block_n;
   const int b_tile_bytes = BN * BLOCK_K * 4;
 
@@ -209,6 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   sm.tmem_full = bars + 3 * MAX_STAGES;
   sm.tmem_empty = bars + 3 * MAX_STAGES + 2;
   sm.tmem_ptr = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
+  static_assert(BK == 16 || BK == 32, "k-block is one 64- or 128-byte swizzle row");
 
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                              : (2 * BN <= 256) ? 256 : 512;
@@ -273,10 +286,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           mbar_wait(&sm.full_a[stage], phase);
           mbar_wait(&sm.full_b[stage], phase);
           tc_fence_after();
-          const uint64_t ah = make_desc_sw128(smem_u32(sm.a_hi[stage]));
-          const uint64_t al = make_desc_sw128(smem_u32(sm.a_lo[stage]));
-          const uint64_t bh = make_desc_sw128(smem_u32(sm.b_hi[stage]));
-          const uint64_t bl = make_desc_sw128(smem_u32(sm.b_lo[stage]));
+          const uint64_t ah = make_desc<BK>(smem_u32(sm.a_hi[stage]));
+          const uint64_t al = make_desc<BK>(smem_u32(sm.a_lo[stage]));
+          const uint64_t bh = make_desc<BK>(smem_u32(sm.b_hi[stage]));
+          const uint64_t bl = make_desc<BK>(smem_u32(sm.b_lo[stage]));
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
             const uint64_t off = (uint64_t)((kk * 32) >> 4);  // 8 tf32 = 32 bytes along K
@@ -304,60 +317,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
   } else if (warp < 6) {
     // ===== A producers: global -> (hi, lo) -> swizzled smem =====
-    const int t = threadIdx.x - 64;  // 0..127
-    const int chunk = t & 7;         // 16-byte chunk within the 128-byte row
-    const int rsub = t >> 3;         // 0..15
+    // Register double buffer: the loads of k-block i+1 are in flight while k-block i is
+    // split and stored, so the producers' global-load latency overlaps their own stores
+    // and the wait for a free stage.
+    constexpr int CH = BK / 4;          // 16-byte chunks per row
+    constexpr int RPP = 128 / CH;       // rows covered per pass of the 128 producer threads
+    const int t = threadIdx.x - 64;     // 0..127
+    const int chunk = t % CH;
+    const int rsub = t / CH;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    float4 cur[CH], nxt[CH];
+    auto issue = [&](float4 (&v)[CH], int tile, int kb) {
       const int64_t m0 = (int64_t)(tile / p.num_n_tiles) * BLOCK_M;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int k0 = kb * BLOCK_K;
-        const float *src;
-        int64_t ld;
-        if (k0 < g.K1) {
-          src = g.A1 + k0;
-          ld = g.lda1;
-        } else {
-          src = g.A2 + (k0 - g.K1);
-          ld = g.lda2;
-        }
-        float4 v[8];
+      const int k0 = kb * BLOCK_K;
+      const float *src;
+      int64_t ld;
+      if (k0 < g.K1) {
+        src = g.A1 + k0;
+        ld = g.lda1;
+      } else {
+        src = g.A2 + (k0 - g.K1);
+        ld = g.lda2;
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t row = m0 + i * 16 + rsub;
-          v[i] = row < g.M ? __ldg(reinterpret_cast<const float4 *>(src + row * ld) + chunk)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        mbar_wait(&sm.empty[stage], phase ^ 1);
-        uint8_t *hi = sm.a_hi[stage], *lo = sm.a_lo[stage];
+      for (int i = 0; i < CH; ++i) {
+        const int64_t row = m0 + i * RPP + rsub;
+        v[i] = row < g.M ? __ldg(reinterpret_cast<const float4 *>(src + row * ld) + chunk)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int tile = blockIdx.x, kb = 0;
+    if (tile < num_tiles) issue(nxt, tile, 0);
+    while (tile < num_tiles) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 16 + rsub;
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-          float4 h;
-          h.x = __uint_as_float((__float_as_uint(v[i].x) + 0x1000u) & 0xFFFFE000u);
-          h.y = __uint_as_float((__float_as_uint(v[i].y) + 0x1000u) & 0xFFFFE000u);
-          h.z = __uint_as_float((__float_as_uint(v[i].z) + 0x1000u) & 0xFFFFE000u);
-          h.w = __uint_as_float((__float_as_uint(v[i].w) + 0x1000u) & 0xFFFFE000u);
-          *reinterpret_cast<float4 *>(hi + off) = h;
-          if (!p.single_pass) {
-            float4 l;
-            l.x = v[i].x - h.x;
-            l.y = v[i].y - h.y;
-            l.z = v[i].z - h.z;
-            l.w = v[i].w - h.w;
-            *reinterpret_cast<float4 *>(lo + off) = l;
-          }
-        }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.full_a[stage]);
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1;
+      for (int i = 0; i < CH; ++i) cur[i] = nxt[i];
+      int ntile = tile, nkb = kb + 1;
+      if (nkb == num_kb) {
+        nkb = 0;
+        ntile = tile + gridDim.x;
+      }
+      if (ntile < num_tiles) issue(nxt, ntile, nkb);
+      mbar_wait(&sm.empty[stage], phase ^ 1);
+      uint8_t *hi = sm.a_hi[stage], *lo = sm.a_lo[stage];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const uint32_t off = swz_off<BK>(i * RPP + rsub, chunk);
+        float4 h;
+        h.x = __uint_as_float((__float_as_uint(cur[i].x) + 0x1000u) & 0xFFFFE000u);
+        h.y = __uint_as_float((__float_as_uint(cur[i].y) + 0x1000u) & 0xFFFFE000u);
+        h.z = __uint_as_float((__float_as_uint(cur[i].z) + 0x1000u) & 0xFFFFE000u);
+        h.w = __uint_as_float((__float_as_uint(cur[i].w) + 0x1000u) & 0xFFFFE000u);
+        *reinterpret_cast<float4 *>(hi + off) = h;
+        if (!p.single_pass) {
+          float4 l;
+          l.x = cur[i].x - h.x;
+          l.y = cur[i].y - h.y;
+          l.z = cur[i].z - h.z;
+          l.w = cur[i].w - h.w;
+          *reinterpret_cast<float4 *>(lo + off) = l;
         }
       }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full_a[stage]);
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+      tile = ntile;
+      kb = nkb;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> fused math -> global =====
@@ -480,20 +509,37 @@ int pick_block_n(uint32_t n) {
 struct TcMaps {
   CUtensorMap hi[TC_W_COUNT], lo[TC_W_COUNT];
   int block_n[TC_W_COUNT];
+  int block_k;
 };
 
-template <int EPI>
-cudaError_t launch_epi(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int grid,
-                       size_t smem, cudaStream_t s) {
+// k-block size: 16 floats by default (more, smaller stages); RUVGNN_TC_BK=32 selects 128-byte rows.
+int tc_block_k() {
+  static int bk = 0;
+  if (!bk) {
+    const char *e = getenv("RUVGNN_TC_BK");
+    bk = (e && atoi(e) == 32) ? 32 : 16;
+  }
+  return bk;
+}
+
+template <int EPI, int BK>
+cudaError_t launch_epi_bk(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int grid,
+                          size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, BK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_tc_kernel<EPI><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
+  gemm_tc_kernel<EPI, BK><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
   return cudaGetLastError();
+}
+template <int EPI>
+cudaError_t launch_epi(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int bk,
+                       int grid, size_t smem, cudaStream_t s) {
+  return bk == 32 ? launch_epi_bk<EPI, 32>(hi, lo, p, grid, smem, s)
+                  : launch_epi_bk<EPI, 16>(hi, lo, p, grid, smem, s);
 }
 
 }  // namespace
@@ -506,11 +552,11 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
   if (!encode) return cudaSuccess;  // driver too old for TMA descriptors: path stays unusable
   size_t total = 0;
   for (int i = 0; i < TC_W_COUNT; ++i) {
-    if (cols[i] % BLOCK_K != 0 || pick_block_n(rows[i]) == 0) return cudaSuccess;
+    if (cols[i] % 32 != 0 || pick_block_n(rows[i]) == 0) return cudaSuccess;
     total += 2 * (size_t)rows[i] * cols[i];
   }
   // the K-concatenated GEMMs switch A source at column H: H itself must be a k-block multiple
-  if (rows[TC_W_O] % BLOCK_K != 0) return cudaSuccess;
+  if (rows[TC_W_O] % 32 != 0) return cudaSuccess;
   std::vector<float> blob(total);
   size_t off = 0;
   size_t offs_hi[TC_W_COUNT], offs_lo[TC_W_COUNT];
@@ -535,6 +581,7 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
   e = cudaMemcpy(out->blob, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   TcMaps *maps = new TcMaps();
+  maps->block_k = tc_block_k();
   for (int i = 0; i < TC_W_COUNT; ++i) {
     out->hi[i] = out->blob + offs_hi[i];
     out->lo[i] = out->blob + offs_lo[i];
@@ -543,12 +590,13 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
     maps->block_n[i] = pick_block_n(rows[i]);
     const cuuint64_t dims[2] = {cols[i], rows[i]};
     const cuuint64_t strides[1] = {(cuuint64_t)cols[i] * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)maps->block_n[i]};
+    const cuuint32_t box[2] = {(cuuint32_t)maps->block_k, (cuuint32_t)maps->block_n[i]};
     const cuuint32_t estr[2] = {1, 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = encode(part ? &maps->lo[i] : &maps->hi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                           part ? out->lo[i] : out->hi[i], dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          maps->block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         delete maps;
@@ -577,8 +625,10 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
   const TcMaps *maps = static_cast<const TcMaps *>(w.tmaps);
   if (!w.usable || !maps) return cudaErrorNotSupported;
   if ((uint32_t)g.N != w.rows[which] || (uint32_t)(g.K1 + g.K2) != w.cols[which] ||
-      g.K1 % BLOCK_K != 0 || g.K2 % BLOCK_K != 0)
+      g.K1 % 32 != 0 || g.K2 % 32 != 0)
     return cudaErrorInvalidValue;
+  const int BLOCK_K = maps->block_k;
+  const int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;
   TcParams p;
   p.g = g;
   p.block_n = maps->block_n[which];
@@ -595,12 +645,14 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
   const int grid = (int)(tiles < sm_count ? tiles : sm_count);
   if (launches) ++*launches;
   switch (epi) {
-    case EPI_BIAS: return launch_epi<EPI_BIAS>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+    case EPI_BIAS:
+      return launch_epi<EPI_BIAS>(maps->hi[which], maps->lo[which], p, BLOCK_K, grid, smem, s);
     case EPI_BIAS_ADD:
-      return launch_epi<EPI_BIAS_ADD>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+      return launch_epi<EPI_BIAS_ADD>(maps->hi[which], maps->lo[which], p, BLOCK_K, grid, smem, s);
     case EPI_GATES:
-      return launch_epi<EPI_GATES>(maps->hi[which], maps->lo[which], p, grid, smem, s);
-    case EPI_GRU: return launch_epi<EPI_GRU>(maps->hi[which], maps->lo[which], p, grid, smem, s);
+      return launch_epi<EPI_GATES>(maps->hi[which], maps->lo[which], p, BLOCK_K, grid, smem, s);
+    case EPI_GRU:
+      return launch_epi<EPI_GRU>(maps->hi[which], maps->lo[which], p, BLOCK_K, grid, smem, s);
   }
   return cudaErrorInvalidValue;
 }
