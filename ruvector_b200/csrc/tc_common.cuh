@@ -1,0 +1,237 @@
+// Shared device helpers of the tcgen05 GEMM kernels (1-CTA and CTA-pair variants).
+#pragma once
+#include <cuda.h>
+
+#include "gemm_tc.cuh"
+
+namespace ruvgnn {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 320;
+constexpr int MAX_STAGES = 8;
+
+struct TcParams {
+  GemmArgs g;
+  int block_n;
+  int stages;
+  int single_pass;
+  int num_m_tiles, num_n_tiles;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A protocol bug must fail fast, never hang the device: trap after 4 s of waiting.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    uint64_t t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major swizzled operand tile: rows of BK*4 bytes (128 or 64), 8-row groups contiguous.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout [61,64): SWIZZLE_128B=2, SWIZZLE_64B=4.)
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                   // LBO (ignored for swizzled K-major), canonical 1
+  d |= (uint64_t)((8 * BK * 4) >> 4) << 32;  // SBO = bytes between 8-row groups
+  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+  d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;  // SWIZZLE_128B / SWIZZLE_64B
+  return d;
+}
+// Byte offset of 16-byte chunk `chunk` of row `r` inside a swizzled tile (what TMA produces
+// for CU_TENSOR_MAP_SWIZZLE_128B / _64B: address bits [4,7) ^= [7,10), resp. [4,6) ^= [7,9)).
+template <int BK>
+__device__ __forceinline__ uint32_t swz_off(int r, int chunk) {
+  if (BK == 32) return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+  return (uint32_t)r * 64u + (uint32_t)((chunk ^ ((r >> 1) & 3)) << 4);
+}
+// cute::UMMA::InstrDescriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ float sigmoid_ref(float x) {  // layer.rs:278-285
+  if (x > 0.f) return 1.0f / (1.0f + expf(-x));
+  const float ex = expf(x);
+  return ex / (1.0f + ex);
+}
+
+
+// Fused epilogue of one 32-column chunk of one output row (thread-per-row after tcgen05.ld).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row, int col,
+                                               float (&v)[32]) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
+    if (EPI == EPI_BIAS) {
+      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if (EPI == EPI_BIAS_ADD) {
+      const float4 *a = reinterpret_cast<const float4 *>(g.add + row * g.ldadd + col);
+      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = a[j];
+        o[j] = make_float4(v[4 * j] + x.x, v[4 * j + 1] + x.y, v[4 * j + 2] + x.z,
+                           v[4 * j + 3] + x.w);
+      }
+    } else if (EPI == EPI_GATES) {
+      if (col < g.H) {
+        float4 *o = reinterpret_cast<float4 *>(g.z + row * g.ldz + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(sigmoid_ref(v[4 * j]), sigmoid_ref(v[4 * j + 1]),
+                             sigmoid_ref(v[4 * j + 2]), sigmoid_ref(v[4 * j + 3]));
+      } else {
+        const int cc = col - g.H;
+        const float4 *m = reinterpret_cast<const float4 *>(g.m + row * g.ldm + cc);
+        float4 *o = reinterpret_cast<float4 *>(g.rh + row * g.ldrh + cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = m[j];
+          o[j] = make_float4(sigmoid_ref(v[4 * j]) * x.x, sigmoid_ref(v[4 * j + 1]) * x.y,
+                             sigmoid_ref(v[4 * j + 2]) * x.z, sigmoid_ref(v[4 * j + 3]) * x.w);
+        }
+      }
+    } else {  // EPI_GRU
+      const float4 *z4 = reinterpret_cast<const float4 *>(g.z + row * g.ldz + col);
+      const float4 *m4 = reinterpret_cast<const float4 *>(g.m + row * g.ldm + col);
+      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 z = z4[j], m = m4[j];
+        float4 r;
+        r.x = ((1.0f - z.x) * m.x + z.x * tanhf(v[4 * j + 0])) * g.keep;
+        r.y = ((1.0f - z.y) * m.y + z.y * tanhf(v[4 * j + 1])) * g.keep;
+        r.z = ((1.0f - z.z) * m.z + z.z * tanhf(v[4 * j + 2])) * g.keep;
+        r.w = ((1.0f - z.w) * m.w + z.w * tanhf(v[4 * j + 3])) * g.keep;
+        o[j] = r;
+      }
+    }
+  }
+
+// Host: tensor maps of a layer's weight matrices.
+struct TcMaps {
+  CUtensorMap hi[TC_W_COUNT], lo[TC_W_COUNT];    // box {block_k, block_n}
+  CUtensorMap hi2[TC_W_COUNT], lo2[TC_W_COUNT];  // box {32, block_n/2}: CTA-pair kernel
+  int block_n[TC_W_COUNT];
+  int block_k;
+  bool pair_ok[TC_W_COUNT];
+};
+
+// CTA-pair (cta_group::2) launcher, gemm_tc2.cu
+cudaError_t launch_gemm_tc_pair(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
+                                bool single_pass, int sm_count, cudaStream_t s);
+
+}  // namespace tc
+}  // namespace ruvgnn
