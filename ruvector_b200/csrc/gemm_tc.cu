@@ -72,6 +72,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   sm.tmem_full = bars + 3 * MAX_STAGES;
   sm.tmem_empty = bars + 3 * MAX_STAGES + 2;
   sm.tmem_ptr = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
+  float *stile = reinterpret_cast<float *>(bars + 3 * MAX_STAGES + 6) + (warp >= 6 ? warp - 6 : 0) * EPI_TILE_FLOATS;
   static_assert(BK == 16 || BK == 32, "k-block is one 64- or 128-byte swizzle row");
 
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -110,10 +111,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
           const uint32_t bytes = p.single_pass ? b_tile_bytes : 2 * b_tile_bytes;
-          mbar_arrive_expect_tx(&sm.full_b[stage], bytes);
-          tma_load_2d(sm.b_hi[stage], &map_hi, &sm.full_b[stage], kb * BLOCK_K, n0);
-          if (!p.single_pass)
-            tma_load_2d(sm.b_lo[stage], &map_lo, &sm.full_b[stage], kb * BLOCK_K, n0);
+          if (p.debug & 2) {
+            mbar_arrive(&sm.full_b[stage]);
+          } else {
+            mbar_arrive_expect_tx(&sm.full_b[stage], bytes);
+            tma_load_2d(sm.b_hi[stage], &map_hi, &sm.full_b[stage], kb * BLOCK_K, n0);
+            if (!p.single_pass)
+              tma_load_2d(sm.b_lo[stage], &map_lo, &sm.full_b[stage], kb * BLOCK_K, n0);
+          }
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -145,7 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
             const uint64_t off = (uint64_t)((kk * 32) >> 4);  // 8 tf32 = 32 bytes along K
             const uint32_t first = (kb | kk) ? 1u : 0u;
-            if (p.single_pass) {
+            if (p.debug & 4) {
+            } else if (p.single_pass) {
               umma_tf32(d, ah + off, bh + off, idesc, first);
             } else {
               umma_tf32(d, al + off, bh + off, idesc, first);
@@ -199,7 +205,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       }
     };
     int tile = blockIdx.x, kb = 0;
-    if (tile < num_tiles) issue(nxt, tile, 0);
+    if (tile < num_tiles && !(p.debug & 1)) issue(nxt, tile, 0);
+    if (p.debug & 1)
+      for (int i = 0; i < CH; ++i) nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     while (tile < num_tiles) {
 #pragma unroll
       for (int i = 0; i < CH; ++i) cur[i] = nxt[i];
@@ -208,11 +216,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         nkb = 0;
         ntile = tile + gridDim.x;
       }
-      if (ntile < num_tiles) issue(nxt, ntile, nkb);
+      if (ntile < num_tiles && !(p.debug & 1)) issue(nxt, ntile, nkb);
       mbar_wait(&sm.empty[stage], phase ^ 1);
       uint8_t *hi = sm.a_hi[stage], *lo = sm.a_lo[stage];
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
+        if (p.debug & 1) break;
         const uint32_t off = swz_off<BK>(i * RPP + rsub, chunk);
         float4 h;
         h.x = __uint_as_float((__float_as_uint(cur[i].x) + 0x1000u) & 0xFFFFE000u);
@@ -251,12 +260,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       mbar_wait(&sm.tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      const bool live = row < g.M;
+      const int64_t row0 = row - lane;  // first row of this warp's 32-row slab
       for (int c = 0; c < BN; c += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        if (!live) continue;
-        epilogue_chunk<EPI>(g, row, n0 + c, v);
+        if (row0 >= g.M || (p.debug & 8)) continue;
+        epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -450,14 +459,23 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
   p.g = g;
   p.block_n = maps->block_n[which];
   p.single_pass = single_pass ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char *e = getenv("RUVGNN_TC_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   p.num_m_tiles = (int)((g.M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_tiles = g.N / p.block_n;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.block_n * BLOCK_K * 4;
-  int stages = (int)((220 * 1024) / stage_bytes);
+  const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * EPI_TILE_FLOATS * sizeof(float);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return cudaErrorInvalidValue;
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = stages * stage_bytes + fixed;
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(tiles < sm_count ? tiles : sm_count);
   if (launches) ++*launches;

@@ -104,6 +104,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
   uint64_t *full_a = bars, *full_b = bars + MAX_STAGES, *empty = bars + 2 * MAX_STAGES;
   uint64_t *tmem_full = bars + 3 * MAX_STAGES, *tmem_empty = bars + 3 * MAX_STAGES + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
+  float *stile = reinterpret_cast<float *>(bars + 3 * MAX_STAGES + 6) + (warp >= 6 ? warp - 6 : 0) * EPI_TILE_FLOATS;
 
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                              : (2 * BN <= 256) ? 256 : 512;
@@ -281,12 +282,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      const bool live = row < g.M;
+      const int64_t row0 = row - lane;  // first row of this warp's 32-row slab
       for (int c = 0; c < BN; c += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        if (!live) continue;
-        epilogue_chunk<EPI>(g, row, n0 + c, v);
+        if (row0 >= g.M) continue;
+        epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -329,14 +330,16 @@ cudaError_t launch_gemm_tc_pair(const GemmArgs &g, EpiKind epi, const TcMaps &ma
   p.g = g;
   p.block_n = maps.block_n[which];
   p.single_pass = single_pass ? 1 : 0;
+  p.debug = 0;
   p.num_m_tiles = (int)((g.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
   p.num_n_tiles = g.N / p.block_n;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)(p.block_n / 2) * BK * 4;
-  int stages = (int)((220 * 1024) / stage_bytes);
+  const size_t fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * EPI_TILE_FLOATS * sizeof(float);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return cudaErrorInvalidValue;
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + 256;
+  const size_t smem = stages * stage_bytes + fixed;
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
   int pairs = sm_count / 2;
   if (tiles < pairs) pairs = (int)tiles;

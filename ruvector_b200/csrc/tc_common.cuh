@@ -17,6 +17,8 @@ struct TcParams {
   int stages;
   int single_pass;
   int num_m_tiles, num_n_tiles;
+  int debug;  // timing experiments only (RUVGNN_TC_DEBUG): 1 = skip A loads/stores, 2 = skip weight TMA,
+              // 4 = skip the MMAs, 8 = skip the epilogue's global traffic.  Results are garbage.
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------
@@ -158,67 +160,58 @@ __device__ __forceinline__ float sigmoid_ref(float x) {  // layer.rs:278-285
 }
 
 
-// Fused epilogue of one 32-column chunk of one output row (thread-per-row after tcgen05.ld).
+// Fused epilogue of one 32-row x 32-column accumulator chunk owned by one warp.
+// tcgen05.ld hands every lane one ROW (32 consecutive columns in registers); touching global
+// memory in that shape costs 32 wavefronts per access.  The chunk is therefore transposed
+// through a padded per-warp shared tile (row stride 36 floats: conflict-free 128-bit row
+// writes and 32-bit column reads) so that lane l owns COLUMN col+l and every global load /
+// store of the warp is one coalesced 128-byte row segment.
+constexpr int EPI_TILE_FLOATS = 32 * 36;  // per epilogue warp
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row, int col,
-                                               float (&v)[32]) {
-    const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + col);
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row0, int col,
+                                               const float (&v)[32], float *stile, int lane) {
+  __syncwarp();  // the previous chunk's column reads are done
+  float4 *dst = reinterpret_cast<float4 *>(stile + lane * 36);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x;
-      v[4 * j + 1] += b.y;
-      v[4 * j + 2] += b.z;
-      v[4 * j + 3] += b.w;
+  for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const float bias = __ldg(g.bias + col + lane);
+  int64_t rows = g.M - row0;
+  if (rows > 32) rows = 32;
+  const int c = col + lane;
+  if (EPI == EPI_BIAS) {
+    float *o = g.out + row0 * g.ldo + c;
+#pragma unroll 8
+    for (int r = 0; r < (int)rows; ++r) o[r * g.ldo] = stile[r * 36 + lane] + bias;
+  } else if (EPI == EPI_BIAS_ADD) {
+    const float *a = g.add + row0 * g.ldadd + c;
+    float *o = g.out + row0 * g.ldo + c;
+#pragma unroll 8
+    for (int r = 0; r < (int)rows; ++r) o[r * g.ldo] = stile[r * 36 + lane] + bias + a[r * g.ldadd];
+  } else if (EPI == EPI_GATES) {
+    if (col < g.H) {
+      float *o = g.z + row0 * g.ldz + c;
+#pragma unroll 8
+      for (int r = 0; r < (int)rows; ++r) o[r * g.ldz] = sigmoid_ref(stile[r * 36 + lane] + bias);
+    } else {
+      const float *m = g.m + row0 * g.ldm + (c - g.H);
+      float *o = g.rh + row0 * g.ldrh + (c - g.H);
+#pragma unroll 8
+      for (int r = 0; r < (int)rows; ++r)
+        o[r * g.ldrh] = sigmoid_ref(stile[r * 36 + lane] + bias) * m[r * g.ldm];
     }
-    if (EPI == EPI_BIAS) {
-      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else if (EPI == EPI_BIAS_ADD) {
-      const float4 *a = reinterpret_cast<const float4 *>(g.add + row * g.ldadd + col);
-      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 x = a[j];
-        o[j] = make_float4(v[4 * j] + x.x, v[4 * j + 1] + x.y, v[4 * j + 2] + x.z,
-                           v[4 * j + 3] + x.w);
-      }
-    } else if (EPI == EPI_GATES) {
-      if (col < g.H) {
-        float4 *o = reinterpret_cast<float4 *>(g.z + row * g.ldz + col);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = make_float4(sigmoid_ref(v[4 * j]), sigmoid_ref(v[4 * j + 1]),
-                             sigmoid_ref(v[4 * j + 2]), sigmoid_ref(v[4 * j + 3]));
-      } else {
-        const int cc = col - g.H;
-        const float4 *m = reinterpret_cast<const float4 *>(g.m + row * g.ldm + cc);
-        float4 *o = reinterpret_cast<float4 *>(g.rh + row * g.ldrh + cc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x = m[j];
-          o[j] = make_float4(sigmoid_ref(v[4 * j]) * x.x, sigmoid_ref(v[4 * j + 1]) * x.y,
-                             sigmoid_ref(v[4 * j + 2]) * x.z, sigmoid_ref(v[4 * j + 3]) * x.w);
-        }
-      }
-    } else {  // EPI_GRU
-      const float4 *z4 = reinterpret_cast<const float4 *>(g.z + row * g.ldz + col);
-      const float4 *m4 = reinterpret_cast<const float4 *>(g.m + row * g.ldm + col);
-      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 z = z4[j], m = m4[j];
-        float4 r;
-        r.x = ((1.0f - z.x) * m.x + z.x * tanhf(v[4 * j + 0])) * g.keep;
-        r.y = ((1.0f - z.y) * m.y + z.y * tanhf(v[4 * j + 1])) * g.keep;
-        r.z = ((1.0f - z.z) * m.z + z.z * tanhf(v[4 * j + 2])) * g.keep;
-        r.w = ((1.0f - z.w) * m.w + z.w * tanhf(v[4 * j + 3])) * g.keep;
-        o[j] = r;
-      }
+  } else {  // EPI_GRU (layer.rs:266-274, 448-451)
+    const float *z = g.z + row0 * g.ldz + c;
+    const float *m = g.m + row0 * g.ldm + c;
+    float *o = g.out + row0 * g.ldo + c;
+#pragma unroll 8
+    for (int r = 0; r < (int)rows; ++r) {
+      const float zz = z[r * g.ldz], mm = m[r * g.ldm];
+      o[r * g.ldo] = ((1.0f - zz) * mm + zz * tanhf(stile[r * 36 + lane] + bias)) * g.keep;
     }
   }
+}
 
 // Host: tensor maps of a layer's weight matrices.
 struct TcMaps {
