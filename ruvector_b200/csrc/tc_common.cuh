@@ -177,38 +177,46 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row0, 
   for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
   const float bias = __ldg(g.bias + col + lane);
-  int64_t rows = g.M - row0;
-  if (rows > 32) rows = 32;
+  int64_t rows64 = g.M - row0;
+  const int rows = rows64 > 32 ? 32 : (int)rows64;
   const int c = col + lane;
-  if (EPI == EPI_BIAS) {
-    float *o = g.out + row0 * g.ldo + c;
-#pragma unroll 8
-    for (int r = 0; r < (int)rows; ++r) o[r * g.ldo] = stile[r * 36 + lane] + bias;
-  } else if (EPI == EPI_BIAS_ADD) {
-    const float *a = g.add + row0 * g.ldadd + c;
-    float *o = g.out + row0 * g.ldo + c;
-#pragma unroll 8
-    for (int r = 0; r < (int)rows; ++r) o[r * g.ldo] = stile[r * 36 + lane] + bias + a[r * g.ldadd];
-  } else if (EPI == EPI_GATES) {
-    if (col < g.H) {
-      float *o = g.z + row0 * g.ldz + c;
-#pragma unroll 8
-      for (int r = 0; r < (int)rows; ++r) o[r * g.ldz] = sigmoid_ref(stile[r * 36 + lane] + bias);
-    } else {
-      const float *m = g.m + row0 * g.ldm + (c - g.H);
-      float *o = g.rh + row0 * g.ldrh + (c - g.H);
-#pragma unroll 8
-      for (int r = 0; r < (int)rows; ++r)
-        o[r * g.ldrh] = sigmoid_ref(stile[r * 36 + lane] + bias) * m[r * g.ldm];
+  // Rows are processed 8 at a time with every load of the group issued before the first
+  // store, so the global-load latency is paid once per group, not once per row.
+  constexpr int G = 8;
+  for (int r0 = 0; r0 < rows; r0 += G) {
+    float acc[G], x1[G], x2[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int r = r0 + k;
+      acc[k] = stile[(r & 31) * 36 + lane] + bias;
+      x1[k] = 0.f;
+      x2[k] = 0.f;
+      if (r < rows) {
+        if (EPI == EPI_BIAS_ADD) x1[k] = __ldg(g.add + (row0 + r) * g.ldadd + c);
+        if (EPI == EPI_GATES && col >= g.H) x1[k] = __ldg(g.m + (row0 + r) * g.ldm + (c - g.H));
+        if (EPI == EPI_GRU) {
+          x1[k] = __ldg(g.z + (row0 + r) * g.ldz + c);
+          x2[k] = __ldg(g.m + (row0 + r) * g.ldm + c);
+        }
+      }
     }
-  } else {  // EPI_GRU (layer.rs:266-274, 448-451)
-    const float *z = g.z + row0 * g.ldz + c;
-    const float *m = g.m + row0 * g.ldm + c;
-    float *o = g.out + row0 * g.ldo + c;
-#pragma unroll 8
-    for (int r = 0; r < (int)rows; ++r) {
-      const float zz = z[r * g.ldz], mm = m[r * g.ldm];
-      o[r * g.ldo] = ((1.0f - zz) * mm + zz * tanhf(stile[r * 36 + lane] + bias)) * g.keep;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int r = r0 + k;
+      if (r >= rows) break;
+      if (EPI == EPI_BIAS) {
+        g.out[(row0 + r) * g.ldo + c] = acc[k];
+      } else if (EPI == EPI_BIAS_ADD) {
+        g.out[(row0 + r) * g.ldo + c] = acc[k] + x1[k];
+      } else if (EPI == EPI_GATES) {
+        const float sg = sigmoid_ref(acc[k]);
+        if (col < g.H)
+          g.z[(row0 + r) * g.ldz + c] = sg;
+        else
+          g.rh[(row0 + r) * g.ldrh + (c - g.H)] = sg * x1[k];
+      } else {  // EPI_GRU (layer.rs:266-274, 448-451)
+        g.out[(row0 + r) * g.ldo + c] = ((1.0f - x1[k]) * x2[k] + x1[k] * tanhf(acc[k])) * g.keep;
+      }
     }
   }
 }
