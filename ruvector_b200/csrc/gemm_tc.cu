@@ -41,7 +41,7 @@ struct SmemLayout {
   uint32_t *tmem_ptr;
 };
 
-template <int EPI, int BK>
+template <int EPI, int BK, bool COAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const TcParams p) {
@@ -265,7 +265,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         float v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
         if (row0 >= g.M || (p.debug & 8)) continue;
-        epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
+        if (COAL) {
+          epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
+        } else if (row < g.M) {
+          epilogue_chunk_rowwise<EPI>(g, row, n0 + c, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -312,12 +316,14 @@ int pick_block_n(uint32_t n) {
 
 // k-block size of the 1-CTA kernel: 32 floats (128-byte rows) by default; RUVGNN_TC_BK=16
 // selects 64-byte rows (more, smaller stages) -- measured slower, kept for experiments.
-// CTA-pair (cta_group::2) kernel on by default; RUVGNN_TC_PAIR=0 forces the 1-CTA kernel.
+// CTA-pair (cta_group::2) kernel: correct (tests run it) but measured ~7% slower than the
+// 1-CTA kernel at config 2 (the per-k-block handshake crosses the cluster), so it is opt-in:
+// RUVGNN_TC_PAIR=1.
 bool tc_pair_enabled() {
   static int on = -1;
   if (on < 0) {
     const char *e = getenv("RUVGNN_TC_PAIR");
-    on = (e && atoi(e) == 0) ? 0 : 1;
+    on = (e && atoi(e) == 1) ? 1 : 0;
   }
   return on == 1;
 }
@@ -330,27 +336,42 @@ int tc_block_k() {
   return bk;
 }
 
-template <int EPI, int BK>
+template <int EPI, int BK, bool COAL>
 cudaError_t launch_epi_bk(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int grid,
                           size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, BK>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, BK, COAL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_tc_kernel<EPI, BK><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
+  gemm_tc_kernel<EPI, BK, COAL><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
   return cudaGetLastError();
 }
 template <int EPI>
 cudaError_t launch_epi(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int bk,
                        int grid, size_t smem, cudaStream_t s) {
-  return bk == 32 ? launch_epi_bk<EPI, 32>(hi, lo, p, grid, smem, s)
-                  : launch_epi_bk<EPI, 16>(hi, lo, p, grid, smem, s);
+  const bool coal = (tc_epi_mask() >> EPI) & 1;
+  if (bk == 32)
+    return coal ? launch_epi_bk<EPI, 32, true>(hi, lo, p, grid, smem, s)
+                : launch_epi_bk<EPI, 32, false>(hi, lo, p, grid, smem, s);
+  return coal ? launch_epi_bk<EPI, 16, true>(hi, lo, p, grid, smem, s)
+              : launch_epi_bk<EPI, 16, false>(hi, lo, p, grid, smem, s);
 }
 
 }  // namespace
+
+namespace tc {
+int tc_epi_mask() {
+  static int mask = -1;
+  if (mask < 0) {
+    const char *e = getenv("RUVGNN_TC_EPI_MASK");
+    mask = e ? atoi(e) : ((1 << EPI_BIAS) | (1 << EPI_GRU));
+  }
+  return mask;
+}
+}  // namespace tc
 
 cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
                               const uint32_t rows[TC_W_COUNT], const uint32_t cols[TC_W_COUNT],

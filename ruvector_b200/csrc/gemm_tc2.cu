@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t make_idesc_tf32_pair(int n) {
 constexpr int BK = 32;
 constexpr int A_TILE_BYTES = BLOCK_M * BK * 4;
 
-template <int EPI>
+template <int EPI, bool COAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
                     const __grid_constant__ CUtensorMap map_lo, const TcParams p) {
@@ -287,7 +287,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
         float v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
         if (row0 >= g.M) continue;
-        epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
+        if (COAL) {
+          epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
+        } else if (row < g.M) {
+          epilogue_chunk_rowwise<EPI>(g, row, n0 + c, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -313,12 +317,18 @@ cudaError_t launch_pair_epi(const CUtensorMap &hi, const CUtensorMap &lo, const 
                             size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<EPI, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tc_pair_kernel<EPI, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_tc_pair_kernel<EPI><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
+  if ((tc_epi_mask() >> EPI) & 1)
+    gemm_tc_pair_kernel<EPI, true><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
+  else
+    gemm_tc_pair_kernel<EPI, false><<<grid, NUM_THREADS, smem, s>>>(hi, lo, p);
   return cudaGetLastError();
 }
 

@@ -180,9 +180,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row0, 
   int64_t rows64 = g.M - row0;
   const int rows = rows64 > 32 ? 32 : (int)rows64;
   const int c = col + lane;
-  // Rows are processed 8 at a time with every load of the group issued before the first
-  // store, so the global-load latency is paid once per group, not once per row.
-  constexpr int G = 8;
+  // All 32 rows of the chunk are loaded before the first store (G = rows per load batch),
+  // so the global-load latency is paid once per chunk, not once per row.
+  constexpr int G = 32;
   for (int r0 = 0; r0 < rows; r0 += G) {
     float acc[G], x1[G], x2[G];
 #pragma unroll
@@ -221,6 +221,71 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row0, 
   }
 }
 
+// Row-wise form of the fused epilogue: every lane keeps the ROW tcgen05.ld gave it and
+// accesses global memory with 128-bit loads/stores of its own row (uncoalesced across the
+// warp, but few instructions).  Measured faster for the gate epilogue, slower for plain bias.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_rowwise(const GemmArgs &g, int64_t row, int col,
+                                               float (&v)[32]) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
+    if (EPI == EPI_BIAS) {
+      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if (EPI == EPI_BIAS_ADD) {
+      const float4 *a = reinterpret_cast<const float4 *>(g.add + row * g.ldadd + col);
+      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = a[j];
+        o[j] = make_float4(v[4 * j] + x.x, v[4 * j + 1] + x.y, v[4 * j + 2] + x.z,
+                           v[4 * j + 3] + x.w);
+      }
+    } else if (EPI == EPI_GATES) {
+      if (col < g.H) {
+        float4 *o = reinterpret_cast<float4 *>(g.z + row * g.ldz + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(sigmoid_ref(v[4 * j]), sigmoid_ref(v[4 * j + 1]),
+                             sigmoid_ref(v[4 * j + 2]), sigmoid_ref(v[4 * j + 3]));
+      } else {
+        const int cc = col - g.H;
+        const float4 *m = reinterpret_cast<const float4 *>(g.m + row * g.ldm + cc);
+        float4 *o = reinterpret_cast<float4 *>(g.rh + row * g.ldrh + cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = m[j];
+          o[j] = make_float4(sigmoid_ref(v[4 * j]) * x.x, sigmoid_ref(v[4 * j + 1]) * x.y,
+                             sigmoid_ref(v[4 * j + 2]) * x.z, sigmoid_ref(v[4 * j + 3]) * x.w);
+        }
+      }
+    } else {  // EPI_GRU
+      const float4 *z4 = reinterpret_cast<const float4 *>(g.z + row * g.ldz + col);
+      const float4 *m4 = reinterpret_cast<const float4 *>(g.m + row * g.ldm + col);
+      float4 *o = reinterpret_cast<float4 *>(g.out + row * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 z = z4[j], m = m4[j];
+        float4 r;
+        r.x = ((1.0f - z.x) * m.x + z.x * tanhf(v[4 * j + 0])) * g.keep;
+        r.y = ((1.0f - z.y) * m.y + z.y * tanhf(v[4 * j + 1])) * g.keep;
+        r.z = ((1.0f - z.z) * m.z + z.z * tanhf(v[4 * j + 2])) * g.keep;
+        r.w = ((1.0f - z.w) * m.w + z.w * tanhf(v[4 * j + 3])) * g.keep;
+        o[j] = r;
+      }
+    }
+  }
+
+
 // Host: tensor maps of a layer's weight matrices.
 struct TcMaps {
   CUtensorMap hi[TC_W_COUNT], lo[TC_W_COUNT];    // box {block_k, block_n}
@@ -229,6 +294,10 @@ struct TcMaps {
   int block_k;
   bool pair_ok[TC_W_COUNT];
 };
+
+// Which epilogue kinds use the coalesced (smem-transposed) form: bit e = EpiKind e.
+// Default from measurements on B200; RUVGNN_TC_EPI_MASK overrides (experiments).
+int tc_epi_mask();
 
 // CTA-pair (cta_group::2) launcher, gemm_tc2.cu
 cudaError_t launch_gemm_tc_pair(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
