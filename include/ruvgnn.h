@@ -131,6 +131,22 @@ int32_t ruvgnn_pack_neighbours(uint64_t n_nodes, const void *const *lists, const
                                size_t stride, size_t id_offset, size_t dist_offset,
                                uint64_t *row_ptr, uint32_t *col_idx, float *edge_w);
 
+/* Reads an hnsw_rs graph dump (`<basename>.hnsw.graph`, written by Hnsw::file_dump:
+ * Description patches/hnsw_rs/src/hnswio.rs:878-918, PointIndexation :1303-1340,
+ * dump_point :1063-1096; Full and Light modes, description versions 2-4) and exposes each
+ * HNSW level as CSR rows indexed by origin_id, neighbours in stored order.  Host only. */
+typedef struct ruvgnn_hnsw_dump ruvgnn_hnsw_dump;
+int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out);
+void ruvgnn_hnsw_dump_close(ruvgnn_hnsw_dump *d);
+/* n_ids = largest origin_id + 1 (the minimum n_nodes of the CSR). */
+int32_t ruvgnn_hnsw_dump_info(const ruvgnn_hnsw_dump *d, uint64_t *nb_point, uint64_t *n_ids,
+                              uint32_t *nb_layer, uint32_t *max_nb_connection, uint64_t *dimension,
+                              uint32_t *dumpmode, uint64_t *entry_point);
+int32_t ruvgnn_hnsw_dump_level_edges(const ruvgnn_hnsw_dump *d, uint32_t level, uint64_t *n_edges);
+/* row_ptr: [n_nodes+1]; col_idx / edge_w: [level_edges]. */
+int32_t ruvgnn_hnsw_dump_level_csr(const ruvgnn_hnsw_dump *d, uint32_t level, uint64_t n_nodes,
+                                   uint64_t *row_ptr, uint32_t *col_idx, float *edge_w);
+
 /* Uploads a CSR (host arrays; the caller keeps ownership).  Validates
  * row_ptr[0]==0, monotone row_ptr, col_idx < n_cols -> RUVGNN_ERR_INVALID_INPUT.
  * n_cols = number of addressable embedding rows (n_nodes for a single GPU;
@@ -160,6 +176,16 @@ void ruvgnn_graph_destroy(ruvgnn_graph *g);
  * x: [n_nodes][input_dim] row-major, out: [n_nodes][hidden_dim]; must not alias. */
 int32_t ruvgnn_layer_forward(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, const ruvgnn_graph *graph,
                              const float *x, float *out, uint32_t flags);
+
+/* Stacked forward (BASELINE config 3: one RuvectorLayer per HNSW level, applied in the
+ * order given, a full Jacobi barrier between layers -- the batched analogue of the loop
+ * in hierarchical_forward, crates/ruvector-gnn/src/search.rs:117-159):
+ *   h_0 = x;  h_{l+1}[i] = layers[l].forward(h_l[i], [h_l[j] for j in N_l(i)], w_l[i]);  out = h_L.
+ * Requires graphs[l].n_nodes equal for all l and layers[l+1].input_dim == layers[l].hidden_dim
+ * (else RUVGNN_ERR_DIMENSION_MISMATCH).  Intermediates stay in HBM. */
+int32_t ruvgnn_stack_forward(ruvgnn_ctx *ctx, const ruvgnn_layer *const *layers,
+                             const ruvgnn_graph *const *graphs, uint32_t n_layers, const float *x,
+                             float *out, uint32_t flags);
 
 /* Replaces RuvectorLayer::forward(&self, node_embedding, neighbor_embeddings,
  * edge_weights) (layer.rs:379-384) for one node, host buffers.  nbrs is K rows

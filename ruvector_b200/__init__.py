@@ -5,11 +5,11 @@ the C ABI in include/ruvgnn.h; all arithmetic runs in libruvgnn.so (no CPU fallb
 from . import errors
 from .errors import GnnError, LayerConfig, DimensionMismatch, InvalidInput, CudaError
 from .graph import CsrGraph, pack_neighbour_lists, pack_id_distance_lists, batch_to_graph, NEIGHBOUR_DTYPE
-from .layer import Context, DeviceGraph, RuvectorLayer, default_context
+from .layer import Context, DeviceGraph, RuvectorLayer, default_context, forward_stack
 from ._lib import MODE_FP32_SIMT, MODE_FP32_TC, MODE_TF32
 
 __all__ = [
-    "RuvectorLayer", "Context", "DeviceGraph", "CsrGraph", "default_context",
+    "RuvectorLayer", "forward_stack", "Context", "DeviceGraph", "CsrGraph", "default_context",
     "pack_neighbour_lists", "pack_id_distance_lists", "batch_to_graph", "NEIGHBOUR_DTYPE",
     "GnnError", "LayerConfig", "DimensionMismatch", "InvalidInput", "CudaError", "errors",
     "MODE_FP32_SIMT", "MODE_FP32_TC", "MODE_TF32",

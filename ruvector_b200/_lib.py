@@ -49,11 +49,17 @@ SYMBOLS = {
     "ruvgnn_layer_set_mode": (C.c_int32, [_vp, C.c_uint32]),
     "ruvgnn_layer_destroy": (None, [_vp]),
     "ruvgnn_pack_neighbours": (C.c_int32, [C.c_uint64, C.POINTER(_vp), _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u32p, c_float_p]),
+    "ruvgnn_hnsw_dump_open": (C.c_int32, [C.c_char_p, C.POINTER(_vp)]),
+    "ruvgnn_hnsw_dump_close": (None, [_vp]),
+    "ruvgnn_hnsw_dump_info": (C.c_int32, [_vp, _u64p, _u64p, _u32p, _u32p, _u64p, _u32p, _u64p]),
+    "ruvgnn_hnsw_dump_level_edges": (C.c_int32, [_vp, C.c_uint32, _u64p]),
+    "ruvgnn_hnsw_dump_level_csr": (C.c_int32, [_vp, C.c_uint32, C.c_uint64, _u64p, _u32p, c_float_p]),
     "ruvgnn_graph_create": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, _u64p, _u32p, c_float_p, C.c_uint32, C.POINTER(_vp)]),
     "ruvgnn_graph_dims": (C.c_int32, [_vp, _u64p, _u64p, _u64p]),
     "ruvgnn_graph_download": (C.c_int32, [_vp, _u64p, _u32p, c_float_p]),
     "ruvgnn_graph_destroy": (None, [_vp]),
     "ruvgnn_layer_forward": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32]),
+    "ruvgnn_stack_forward": (C.c_int32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.c_uint32, _vp, _vp, C.c_uint32]),
     "ruvgnn_layer_forward_node": (C.c_int32, [_vp, _vp, c_float_p, C.c_uint32, c_float_p, C.c_uint32, c_float_p, C.c_uint32, c_float_p]),
     "ruvgnn_layer_project": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_halo_pack": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),

@@ -37,6 +37,8 @@ struct ruvgnn_ctx {
   // host-pointer staging
   float *x_stage = nullptr, *out_stage = nullptr;
   size_t x_stage_floats = 0, out_stage_floats = 0;
+  float *stack_buf[2] = {nullptr, nullptr};  // ping-pong activations of ruvgnn_stack_forward
+  size_t stack_floats[2] = {0, 0};
   int *d_flag = nullptr;
   // timing ring: every timed forward records 7 events into the next slot;
   // ruvgnn_ctx_last_timing averages the slots recorded since the previous query.
@@ -469,6 +471,8 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
   if (c->ws) cudaFree(c->ws);
   if (c->x_stage) cudaFree(c->x_stage);
   if (c->out_stage) cudaFree(c->out_stage);
+  for (auto &b : c->stack_buf)
+    if (b) cudaFree(b);
   if (c->d_flag) cudaFree(c->d_flag);
   for (auto &slot : c->ring)
     for (auto &ev : slot)
@@ -810,6 +814,68 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
     RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
     if (timing) cudaEventRecord(c->ev[5], c->stream);
   }
+  if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
+                             const ruvgnn_graph *const *graphs, uint32_t n_layers, const float *x,
+                             float *out, uint32_t flags) {
+  if (!c || !layers || !graphs || !x || !out || n_layers == 0)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  const uint64_t n = graphs[0] ? graphs[0]->n_nodes : 0;
+  for (uint32_t l = 0; l < n_layers; ++l) {
+    if (!layers[l] || !graphs[l]) return fail(RUVGNN_ERR_INVALID_INPUT, "null layer / graph");
+    if (layers[l]->device != c->device || graphs[l]->device != c->device)
+      return fail(RUVGNN_ERR_INVALID_INPUT, "layer / graph live on another device than ctx");
+    if (graphs[l]->n_nodes != n || graphs[l]->n_cols != n)
+      return fail(RUVGNN_ERR_DIMENSION_MISMATCH,
+                  "Tensor dimension mismatch: every level graph must cover the same nodes");
+    if (l && layers[l]->D != layers[l - 1]->H) {
+      char buf[128];
+      snprintf(buf, sizeof buf, "Tensor dimension mismatch: expected %u, got %u (layer %u input)",
+               layers[l - 1]->H, layers[l]->D, l);
+      return fail(RUVGNN_ERR_DIMENSION_MISMATCH, buf);
+    }
+  }
+  if (n == 0) return RUVGNN_OK;
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
+  c->timing_valid = false;
+  int32_t rc;
+  uint32_t maxH = 0;
+  for (uint32_t l = 0; l < n_layers; ++l) maxH = layers[l]->H > maxH ? layers[l]->H : maxH;
+  if ((rc = ensure_ws(c, n, maxH))) return rc;
+  const float *cur = x;
+  if (!dev_ptrs) {
+    if ((rc = ensure_stage(c, &c->x_stage, &c->x_stage_floats, (size_t)n * layers[0]->D))) return rc;
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(c->x_stage, x, (size_t)n * layers[0]->D * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->stream));
+    cur = c->x_stage;
+    if ((rc = ensure_stage(c, &c->out_stage, &c->out_stage_floats,
+                           (size_t)n * layers[n_layers - 1]->H)))
+      return rc;
+  } else if (x == out) {
+    return fail(RUVGNN_ERR_INVALID_INPUT, "out must not alias x (Jacobi update)");
+  }
+  float *final_dev = dev_ptrs ? out : c->out_stage;
+  for (uint32_t l = 0; l < n_layers; ++l) {
+    float *dst = final_dev;
+    if (l + 1 < n_layers) {
+      const int b = (int)(l & 1);
+      if ((rc = ensure_stage(c, &c->stack_buf[b], &c->stack_floats[b], (size_t)n * layers[l]->H)))
+        return rc;
+      dst = c->stack_buf[b];
+    }
+    if ((rc = do_project(c, layers[l], n, cur))) return rc;
+    if ((rc = do_aggregate_update(c, layers[l], graphs[l], nullptr, 0, n, dst))) return rc;
+    cur = dst;
+  }
+  if (!dev_ptrs)
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(out, c->out_stage,
+                                    (size_t)n * layers[n_layers - 1]->H * sizeof(float),
+                                    cudaMemcpyDeviceToHost, c->stream));
   if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RUVGNN_OK;
 }

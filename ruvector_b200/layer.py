@@ -327,3 +327,29 @@ class RuvectorLayer:
         flags = _lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.FWD_TIMING if timing else 0)
         _lib.check(_lib.load().ruvgnn_layer_forward(
             self.ctx.handle, self._device_layer(), graph.handle, C.c_void_p(x_ptr), C.c_void_p(out_ptr), flags))
+
+
+def forward_stack(layers: Sequence[RuvectorLayer], x, graphs: Sequence[DeviceGraph], out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Stacked forward, one layer per HNSW level graph, applied in the order given (config 3).
+
+    Batched analogue of the per-level loop of ``hierarchical_forward``
+    (crates/ruvector-gnn/src/search.rs:117-159): the output of layer l is the input of
+    layer l+1, so ``layers[l+1].input_dim`` must equal ``layers[l].hidden_dim``.
+    Host buffers in / out; intermediates stay on the device.
+    """
+    if len(layers) != len(graphs) or not layers:
+        raise InvalidInput("one graph per layer is required")
+    x = np.ascontiguousarray(x, dtype=F32)
+    if x.ndim != 2 or x.shape[1] != layers[0].input_dim:
+        raise DimensionMismatch(f"Tensor dimension mismatch: expected {layers[0].input_dim}, got {x.shape[-1]}")
+    if x.shape[0] != graphs[0].n_nodes:
+        raise DimensionMismatch(f"Tensor dimension mismatch: expected {graphs[0].n_nodes} rows, got {x.shape[0]}")
+    ctx = layers[0].ctx
+    if out is None:
+        out = np.empty((x.shape[0], layers[-1].hidden_dim), dtype=F32)
+    n = len(layers)
+    lh = (C.c_void_p * n)(*[l._device_layer() for l in layers])
+    gh = (C.c_void_p * n)(*[g.handle for g in graphs])
+    _lib.check(_lib.load().ruvgnn_stack_forward(ctx.handle, lh, gh, n, C.c_void_p(x.ctypes.data),
+                                                C.c_void_p(out.ctypes.data), 0))
+    return out

@@ -235,3 +235,37 @@ def test_large_graph_properties_without_the_oracle(ctx):
     m = x[iso] @ layer.weights["w_msg"][0].T
     ln = (m - m.mean(1, keepdims=True)) / np.sqrt(m.var(1, keepdims=True) + 1e-5)
     assert np.abs(out[iso] - ln).max() < 2e-4
+
+
+def test_config3_three_stacked_layers_over_hnsw_levels(oracle, ctx):
+    """BASELINE config 3 (scaled down): 3 RuvectorLayers with distinct weights, one per HNSW
+    level, top-down (level 2, 1, 0).  Nodes absent from an upper level take the LN(W_msg x)
+    branch there.  Checked against the oracle applied layer by layer."""
+    n, d, heads, m = 20_000, 128, 4, 8
+    x = synth.make_features(n, d, seed=301)
+    levels = [2, 1, 0]
+    graphs = [synth.hnsw_like_graph(n, m, seed=302, level=lv, iso_frac=0.01 if lv == 0 else 0.0) for lv in levels]
+    assert graphs[0].n_edges < graphs[1].n_edges < graphs[2].n_edges
+    layers = [rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=310 + i), ctx=ctx)
+              for i in range(3)]
+    for mode in (rv.MODE_FP32_SIMT, rv.MODE_FP32_TC):
+        for l in layers:
+            l.set_mode(mode)
+        out = rv.forward_stack(layers, x, [g.to_device(ctx) for g in graphs])
+        ref = x
+        for l, g in zip(layers, graphs):
+            ref = oracle.forward_graph(l, ref, g)
+        assert_parity(out, ref)
+
+
+def test_stack_rejects_mismatched_dimensions(ctx):
+    a = rv.RuvectorLayer(8, 16, 2, 0.1, ctx=ctx)
+    b = rv.RuvectorLayer(8, 8, 2, 0.1, ctx=ctx)  # expects 16 inputs
+    g = rv.CsrGraph(np.zeros(5, np.uint64), np.zeros(0, np.uint32), np.zeros(0, F32)).to_device(ctx)
+    with pytest.raises(rv.DimensionMismatch) as e:
+        rv.forward_stack([a, b], np.zeros((4, 8), F32), [g, g])
+    assert "expected 16, got 8" in str(e.value)
+    # widths may change between layers when they chain correctly (search.rs:232-241)
+    c = rv.RuvectorLayer(16, 8, 2, 0.1, ctx=ctx)
+    out = rv.forward_stack([a, c], np.ones((4, 8), F32), [g, g])
+    assert out.shape == (4, 8) and np.isfinite(out).all()
