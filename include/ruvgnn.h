@@ -196,6 +196,32 @@ int32_t ruvgnn_layer_forward_node(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, co
                                   uint32_t x_len, const float *nbrs, uint32_t k, const float *w,
                                   uint32_t n_w, float *out);
 
+/* ---- query-time search path (crates/ruvector-gnn/src/search.rs) -------------------- */
+
+/* Batched differentiable_search (search.rs:56-94): for each of n_queries queries, cosine
+ * similarity against all n_cand candidates (f32 dot, f64 norms, :4-26), temperature softmax
+ * over all candidates (:29-44), the k = min(k, n_cand) best by descending weight (ties in
+ * index order).  idx_out / w_out: [n_queries][k_eff], k_eff returned in *k_out.  k <= 16.
+ * Host pointers (RUVGNN_FWD_DEVICE_PTRS: device pointers). */
+int32_t ruvgnn_differentiable_search(ruvgnn_ctx *ctx, const float *queries, uint64_t n_queries,
+                                     const float *cands, uint64_t n_cand, uint32_t dim, uint32_t k,
+                                     float temperature, uint32_t *idx_out, float *w_out,
+                                     uint32_t *k_out, uint32_t flags);
+
+/* Batched hierarchical_forward (search.rs:105-162) for n_queries independent queries:
+ * per level l (skipped when level_rows[l] == 0): top-5 differentiable_search at T = 1 over
+ * level_emb[l] ([level_rows[l]][level_dim[l]]), aggregated = sum w e, combined =
+ * (cur + aggregated)/2, cur = layers[l].forward(combined, selected rows, weights).
+ * level_dim[l] must equal the current width and layers[l].input_dim
+ * (RUVGNN_ERR_DIMENSION_MISMATCH; the reference panics inside ndarray).
+ * out: [n_queries][width after the last applied layer]; *out_dim receives that width.
+ * Host pointers only. */
+int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *ctx, const float *queries, uint64_t n_queries,
+                                    uint32_t query_dim, const float *const *level_emb,
+                                    const uint64_t *level_rows, const uint32_t *level_dim,
+                                    const ruvgnn_layer *const *layers, uint32_t n_levels,
+                                    float *out, uint32_t out_capacity_floats, uint32_t *out_dim);
+
 /* ---- range-partitioned forward (one process per GPU) -------- */
 /* Phase A: project the partition's own rows; x is [n_local][input_dim]
  * (device).  Afterwards ruvgnn_halo_pack gathers the projected K|V|M rows

@@ -122,4 +122,15 @@ cudaError_t launch_validate_csr(const uint64_t *row_ptr, const uint32_t *col_idx
                                 uint64_t n_cols, uint64_t n_edges, int *d_flag, cudaStream_t s,
                                 uint64_t *launches);
 
+// ---- search.cu: batched differentiable_search / hierarchical_forward pieces ---------
+cudaError_t launch_row_norms(const float *x, uint64_t rows, uint32_t dim, float *norms,
+                             cudaStream_t s, uint64_t *launches);
+cudaError_t launch_topk_softmax(float *dots, const float *qnorm, const float *enorm,
+                                uint64_t n_queries, uint64_t n, int k, float temperature,
+                                uint32_t *idx_out, float *w_out, cudaStream_t s,
+                                uint64_t *launches);
+cudaError_t launch_build_batch(const float *cur, const float *emb, const uint32_t *idx,
+                               const float *w, uint64_t nq, int k, uint32_t dim, float *xb,
+                               cudaStream_t s, uint64_t *launches);
+
 }  // namespace ruvgnn

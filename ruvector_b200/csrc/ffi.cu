@@ -975,3 +975,178 @@ int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, cons
 }
 
 }  // extern "C"
+
+namespace {
+
+struct DevBuf {  // RAII device scratch
+  void *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <class T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+};
+
+// similarities + top-k for device-resident queries / candidates
+int32_t search_device(ruvgnn_ctx *c, const float *q_dev, uint64_t nq, const float *e_dev,
+                      uint64_t n, uint32_t dim, int k, float temperature, uint32_t *idx_dev,
+                      float *w_dev) {
+  DevBuf dots, qn, en, zero;
+  RUVGNN_CUDA_TRY(dots.alloc(nq * n * sizeof(float)));
+  RUVGNN_CUDA_TRY(qn.alloc(nq * sizeof(float)));
+  RUVGNN_CUDA_TRY(en.alloc(n * sizeof(float)));
+  RUVGNN_CUDA_TRY(zero.alloc(n * sizeof(float)));
+  RUVGNN_CUDA_TRY(cudaMemsetAsync(zero.p, 0, n * sizeof(float), c->stream));
+  RUVGNN_CUDA_TRY(launch_row_norms(q_dev, nq, dim, qn.as<float>(), c->stream, &c->launches));
+  RUVGNN_CUDA_TRY(launch_row_norms(e_dev, n, dim, en.as<float>(), c->stream, &c->launches));
+  GemmArgs g;  // dots[q][c] = <query q, candidate c>  (FP32 FFMA)
+  g.M = (int64_t)nq;
+  g.N = (int32_t)n;
+  g.K1 = (int32_t)dim;
+  g.A1 = q_dev;
+  g.lda1 = dim;
+  g.W = e_dev;
+  g.bias = zero.as<float>();
+  g.out = dots.as<float>();
+  g.ldo = (int64_t)n;
+  RUVGNN_CUDA_TRY(launch_gemm_simt(g, EPI_BIAS, c->stream, &c->launches));
+  RUVGNN_CUDA_TRY(launch_topk_softmax(dots.as<float>(), qn.as<float>(), en.as<float>(), nq, n, k,
+                                      temperature, idx_dev, w_dev, c->stream, &c->launches));
+  RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RUVGNN_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t ruvgnn_differentiable_search(ruvgnn_ctx *c, const float *queries,
+                                                uint64_t n_queries, const float *cands,
+                                                uint64_t n_cand, uint32_t dim, uint32_t k,
+                                                float temperature, uint32_t *idx_out, float *w_out,
+                                                uint32_t *k_out, uint32_t flags) {
+  if (!c || !k_out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  *k_out = 0;
+  if (n_cand == 0 || n_queries == 0) return RUVGNN_OK;  // search.rs:62-64: empty result
+  if (!queries || !cands || !idx_out || !w_out || dim == 0)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (n_cand > 0x7fffffffull) return fail(RUVGNN_ERR_INVALID_INPUT, "too many candidates");
+  uint32_t ke = k < n_cand ? k : (uint32_t)n_cand;  // search.rs:66
+  if (ke == 0) return RUVGNN_OK;
+  if (ke > 16) return fail(RUVGNN_ERR_INVALID_INPUT, "k > 16 is not supported");
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  const bool dev = flags & RUVGNN_FWD_DEVICE_PTRS;
+  DevBuf qd, ed, id, wd;
+  const float *q_dev = queries, *e_dev = cands;
+  if (!dev) {
+    RUVGNN_CUDA_TRY(qd.alloc(n_queries * dim * sizeof(float)));
+    RUVGNN_CUDA_TRY(ed.alloc(n_cand * dim * sizeof(float)));
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(qd.p, queries, n_queries * dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->stream));
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(ed.p, cands, n_cand * dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->stream));
+    q_dev = qd.as<float>();
+    e_dev = ed.as<float>();
+  }
+  RUVGNN_CUDA_TRY(id.alloc(n_queries * ke * sizeof(uint32_t)));
+  RUVGNN_CUDA_TRY(wd.alloc(n_queries * ke * sizeof(float)));
+  int32_t rc = search_device(c, q_dev, n_queries, e_dev, n_cand, dim, (int)ke, temperature,
+                             id.as<uint32_t>(), wd.as<float>());
+  if (rc) return rc;
+  const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  RUVGNN_CUDA_TRY(cudaMemcpy(idx_out, id.p, n_queries * ke * sizeof(uint32_t), kind));
+  RUVGNN_CUDA_TRY(cudaMemcpy(w_out, wd.p, n_queries * ke * sizeof(float), kind));
+  *k_out = ke;
+  return RUVGNN_OK;
+}
+
+extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queries,
+                                               uint64_t n_queries, uint32_t query_dim,
+                                               const float *const *level_emb,
+                                               const uint64_t *level_rows,
+                                               const uint32_t *level_dim,
+                                               const ruvgnn_layer *const *layers,
+                                               uint32_t n_levels, float *out,
+                                               uint32_t out_capacity_floats, uint32_t *out_dim) {
+  if (!c || !queries || !out || !out_dim) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (n_levels && (!level_emb || !level_rows || !level_dim || !layers))
+    return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  // validate the chain first (the reference would panic inside ndarray on a width mismatch)
+  uint32_t width = query_dim;
+  for (uint32_t l = 0; l < n_levels; ++l) {
+    if (level_rows[l] == 0) continue;  // search.rs:121-123
+    if (!layers[l] || !level_emb[l]) return fail(RUVGNN_ERR_INVALID_INPUT, "null layer / level");
+    if (layers[l]->device != c->device)
+      return fail(RUVGNN_ERR_INVALID_INPUT, "layer lives on another device than ctx");
+    if (level_dim[l] != width || layers[l]->D != width) {
+      char buf[128];
+      snprintf(buf, sizeof buf, "Tensor dimension mismatch: expected %u, got %u (level %u)", width,
+               level_dim[l] != width ? level_dim[l] : layers[l]->D, l);
+      return fail(RUVGNN_ERR_DIMENSION_MISMATCH, buf);
+    }
+    width = layers[l]->H;
+  }
+  *out_dim = width;
+  if (out_capacity_floats < width)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "out buffer is too small for the final width");
+  if (n_queries == 0) return RUVGNN_OK;
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  c->timing_valid = false;
+  const uint64_t nq = n_queries;
+  DevBuf cur, nxt;
+  RUVGNN_CUDA_TRY(cur.alloc(nq * query_dim * sizeof(float)));
+  RUVGNN_CUDA_TRY(cudaMemcpyAsync(cur.p, queries, nq * query_dim * sizeof(float),
+                                  cudaMemcpyHostToDevice, c->stream));
+  width = query_dim;
+  for (uint32_t l = 0; l < n_levels; ++l) {
+    const uint64_t n = level_rows[l];
+    if (n == 0) continue;
+    const ruvgnn_layer *L = layers[l];
+    const int k = n < 5 ? (int)n : 5;  // search.rs:128
+    DevBuf ed, idx, wts, xb, ob;
+    RUVGNN_CUDA_TRY(ed.alloc(n * width * sizeof(float)));
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(ed.p, level_emb[l], n * width * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->stream));
+    RUVGNN_CUDA_TRY(idx.alloc(nq * k * sizeof(uint32_t)));
+    RUVGNN_CUDA_TRY(wts.alloc(nq * k * sizeof(float)));
+    int32_t rc = search_device(c, cur.as<float>(), nq, ed.as<float>(), n, width, k, 1.0f,
+                               idx.as<uint32_t>(), wts.as<float>());
+    if (rc) return rc;
+    // batch = [combined queries ; selected rows]; query q owns edges to rows nq + q*k + j
+    const uint64_t rows = nq * (uint64_t)(k + 1);
+    RUVGNN_CUDA_TRY(xb.alloc(rows * width * sizeof(float)));
+    RUVGNN_CUDA_TRY(launch_build_batch(cur.as<float>(), ed.as<float>(), idx.as<uint32_t>(),
+                                       wts.as<float>(), nq, k, width, xb.as<float>(), c->stream,
+                                       &c->launches));
+    std::vector<uint64_t> rp(rows + 1);
+    std::vector<uint32_t> ci(nq * k);
+    for (uint64_t q = 0; q <= rows; ++q) rp[q] = q < nq ? q * k : nq * k;
+    for (uint64_t e = 0; e < nq * k; ++e) ci[e] = (uint32_t)(nq + e);
+    std::vector<float> ew(nq * k, 1.0f);
+    ruvgnn_graph *G = nullptr;
+    rc = ruvgnn_graph_create(c, rows, rows, rp.data(), ci.data(), ew.data(), 0, &G);
+    if (rc) return rc;
+    // the soft weights are the edge weights (search.rs:156): same [q][j] order as the edges
+    cudaError_t ce = cudaMemcpyAsync(G->edge_w, wts.p, nq * k * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, c->stream);
+    if (ce == cudaSuccess) ce = ob.alloc(nq * L->H * sizeof(float));
+    if (ce != cudaSuccess) {
+      ruvgnn_graph_destroy(G);
+      return fail(RUVGNN_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    rc = do_project(c, L, rows, xb.as<float>());
+    if (!rc) rc = do_aggregate_update(c, L, G, nullptr, 0, nq, ob.as<float>());
+    cudaStreamSynchronize(c->stream);
+    ruvgnn_graph_destroy(G);
+    if (rc) return rc;
+    std::swap(cur.p, ob.p);
+    width = L->H;
+  }
+  RUVGNN_CUDA_TRY(cudaMemcpyAsync(out, cur.p, nq * width * sizeof(float), cudaMemcpyDeviceToHost,
+                                  c->stream));
+  RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RUVGNN_OK;
+}

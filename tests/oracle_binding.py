@@ -54,6 +54,32 @@ class Oracle:
         L.orc_differentiable_search.argtypes = [c_float_p, c_float_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                 C.c_float, u32p, c_float_p]
 
+    def differentiable_search(self, query, cands, k, temperature):
+        q = np.ascontiguousarray(query, dtype=F32)
+        c = np.ascontiguousarray(cands, dtype=F32)
+        idx = np.empty(max(k, 1), dtype=np.uint32)
+        w = np.empty(max(k, 1), dtype=F32)
+        n = self.lib.orc_differentiable_search(_p(q), _p(c), c.shape[0], c.shape[1], k, temperature,
+                                               idx.ctypes.data_as(C.POINTER(C.c_uint32)), _p(w))
+        return idx[:n], w[:n]
+
+    def hierarchical_forward(self, query, level_embs, layers) -> np.ndarray:
+        n = min(len(level_embs), len(layers))
+        embs = [np.ascontiguousarray(e, dtype=F32).reshape(-1, np.asarray(e).shape[-1]) for e in level_embs[:n]]
+        ols = [self.c_layer(l) for l in layers[:n]]
+        eptr = (c_float_p * n)(*[_p(e) for e in embs])
+        rows = (C.c_uint32 * n)(*[e.shape[0] for e in embs])
+        dims = (C.c_uint32 * n)(*[e.shape[1] for e in embs])
+        lptr = (C.POINTER(OrcLayer) * n)(*[C.pointer(o) for o in ols])
+        q = np.ascontiguousarray(query, dtype=F32)
+        out = np.empty(4096, dtype=F32)
+        self.lib.orc_hierarchical_forward.restype = C.c_uint32
+        self.lib.orc_hierarchical_forward.argtypes = [c_float_p, C.c_uint32, C.POINTER(c_float_p), C.POINTER(C.c_uint32),
+                                                      C.POINTER(C.c_uint32), C.POINTER(C.POINTER(OrcLayer)), C.c_uint32,
+                                                      c_float_p]
+        ln = self.lib.orc_hierarchical_forward(_p(q), q.size, eptr, rows, dims, lptr, n, _p(out))
+        return out[:ln].copy()
+
     @staticmethod
     def c_layer(layer) -> OrcLayer:
         """layer: ruvector_b200.RuvectorLayer (only its host weights are read)."""
