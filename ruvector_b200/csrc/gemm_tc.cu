@@ -367,7 +367,7 @@ int tc_epi_mask() {
   static int mask = -1;
   if (mask < 0) {
     const char *e = getenv("RUVGNN_TC_EPI_MASK");
-    mask = e ? atoi(e) : ((1 << EPI_BIAS) | (1 << EPI_GRU));
+    mask = e ? atoi(e) : 15;  // all kinds coalesced (measured: 59.7 ms/layer vs 61.8 row-wise)
   }
   return mask;
 }

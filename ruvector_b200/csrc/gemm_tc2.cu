@@ -259,7 +259,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
           *reinterpret_cast<float4 *>(lo + off) = l;
         }
       }
-      asm volatile("fence.proxy.async;" ::: "memory");  // generic stores -> async proxy (tensor core)
+      fence_proxy_async();  // generic stores -> async proxy (tensor core)
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&full_a[stage]);
       if (++stage == stages) {

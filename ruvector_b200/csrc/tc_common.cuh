@@ -171,52 +171,63 @@ constexpr int EPI_TILE_FLOATS = 32 * 36;  // per epilogue warp
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row0, int col,
                                                const float (&v)[32], float *stile, int lane) {
-  __syncwarp();  // the previous chunk's column reads are done
+  __syncwarp();  // the previous chunk's reads are done
   float4 *dst = reinterpret_cast<float4 *>(stile + lane * 36);
 #pragma unroll
   for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
-  const float bias = __ldg(g.bias + col + lane);
-  int64_t rows64 = g.M - row0;
+  // 8 lanes x float4 cover the 32 columns of one row (128 contiguous bytes); one warp
+  // instruction covers 4 rows; 8 passes cover the 32 rows.  Same instruction count as the
+  // row-wise form, 8x fewer memory wavefronts.
+  const int rs = lane >> 3, c4 = (lane & 7) * 4;
+  const int c = col + c4;
+  const float4 bias = __ldg(reinterpret_cast<const float4 *>(g.bias + c));
+  const int64_t rows64 = g.M - row0;
   const int rows = rows64 > 32 ? 32 : (int)rows64;
-  const int c = col + lane;
-  // All 32 rows of the chunk are loaded before the first store (G = rows per load batch),
-  // so the global-load latency is paid once per chunk, not once per row.
-  constexpr int G = 32;
-  for (int r0 = 0; r0 < rows; r0 += G) {
-    float acc[G], x1[G], x2[G];
+  float4 acc[8], x1[8], x2[8];
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-      const int r = r0 + k;
-      acc[k] = stile[(r & 31) * 36 + lane] + bias;
-      x1[k] = 0.f;
-      x2[k] = 0.f;
-      if (r < rows) {
-        if (EPI == EPI_BIAS_ADD) x1[k] = __ldg(g.add + (row0 + r) * g.ldadd + c);
-        if (EPI == EPI_GATES && col >= g.H) x1[k] = __ldg(g.m + (row0 + r) * g.ldm + (c - g.H));
-        if (EPI == EPI_GRU) {
-          x1[k] = __ldg(g.z + (row0 + r) * g.ldz + c);
-          x2[k] = __ldg(g.m + (row0 + r) * g.ldm + c);
-        }
+  for (int p = 0; p < 8; ++p) {  // every load of the chunk is issued before the first store
+    const int r = p * 4 + rs;
+    const float4 a = *reinterpret_cast<const float4 *>(stile + r * 36 + c4);
+    acc[p] = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+    x1[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    x2[p] = x1[p];
+    if (r < rows) {
+      if (EPI == EPI_BIAS_ADD)
+        x1[p] = __ldg(reinterpret_cast<const float4 *>(g.add + (row0 + r) * g.ldadd + c));
+      if (EPI == EPI_GATES && col >= g.H)
+        x1[p] = __ldg(reinterpret_cast<const float4 *>(g.m + (row0 + r) * g.ldm + (c - g.H)));
+      if (EPI == EPI_GRU) {
+        x1[p] = __ldg(reinterpret_cast<const float4 *>(g.z + (row0 + r) * g.ldz + c));
+        x2[p] = __ldg(reinterpret_cast<const float4 *>(g.m + (row0 + r) * g.ldm + c));
       }
     }
+  }
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-      const int r = r0 + k;
-      if (r >= rows) break;
-      if (EPI == EPI_BIAS) {
-        g.out[(row0 + r) * g.ldo + c] = acc[k];
-      } else if (EPI == EPI_BIAS_ADD) {
-        g.out[(row0 + r) * g.ldo + c] = acc[k] + x1[k];
-      } else if (EPI == EPI_GATES) {
-        const float sg = sigmoid_ref(acc[k]);
-        if (col < g.H)
-          g.z[(row0 + r) * g.ldz + c] = sg;
-        else
-          g.rh[(row0 + r) * g.ldrh + (c - g.H)] = sg * x1[k];
-      } else {  // EPI_GRU (layer.rs:266-274, 448-451)
-        g.out[(row0 + r) * g.ldo + c] = ((1.0f - x1[k]) * x2[k] + x1[k] * tanhf(acc[k])) * g.keep;
-      }
+  for (int p = 0; p < 8; ++p) {
+    const int r = p * 4 + rs;
+    if (r >= rows) continue;
+    const float4 a = acc[p];
+    if (EPI == EPI_BIAS) {
+      *reinterpret_cast<float4 *>(g.out + (row0 + r) * g.ldo + c) = a;
+    } else if (EPI == EPI_BIAS_ADD) {
+      *reinterpret_cast<float4 *>(g.out + (row0 + r) * g.ldo + c) =
+          make_float4(a.x + x1[p].x, a.y + x1[p].y, a.z + x1[p].z, a.w + x1[p].w);
+    } else if (EPI == EPI_GATES) {
+      const float4 sg = make_float4(sigmoid_ref(a.x), sigmoid_ref(a.y), sigmoid_ref(a.z), sigmoid_ref(a.w));
+      if (col < g.H)
+        *reinterpret_cast<float4 *>(g.z + (row0 + r) * g.ldz + c) = sg;
+      else
+        *reinterpret_cast<float4 *>(g.rh + (row0 + r) * g.ldrh + (c - g.H)) =
+            make_float4(sg.x * x1[p].x, sg.y * x1[p].y, sg.z * x1[p].z, sg.w * x1[p].w);
+    } else {  // EPI_GRU (layer.rs:266-274, 448-451)
+      const float4 z = x1[p], m = x2[p];
+      float4 o;
+      o.x = ((1.0f - z.x) * m.x + z.x * tanhf(a.x)) * g.keep;
+      o.y = ((1.0f - z.y) * m.y + z.y * tanhf(a.y)) * g.keep;
+      o.z = ((1.0f - z.z) * m.z + z.z * tanhf(a.z)) * g.keep;
+      o.w = ((1.0f - z.w) * m.w + z.w * tanhf(a.w)) * g.keep;
+      *reinterpret_cast<float4 *>(g.out + (row0 + r) * g.ldo + c) = o;
     }
   }
 }
