@@ -124,22 +124,64 @@ def exchange_rows(plan: HaloPlan, send_rows, group=None):
     return halo
 
 
-class Partition:
-    """Device-side state of one rank: plan, device CSR, send indices, buffers."""
+def choose_dense(plan: HaloPlan, threshold: float = 0.75, group=None) -> bool:
+    """Collective decision: when every rank needs at least ``threshold`` of all remote rows
+    (random graphs), one all-gather of the projected block beats the de-duplicated
+    all-to-all-v (no per-peer send copies).  Needs equal partition sizes."""
+    import torch
+    import torch.distributed as dist
 
-    def __init__(self, plan: HaloPlan, ctx):
+    if plan.world == 1:
+        return False
+    sizes = np.diff(plan.bounds)
+    equal = bool((sizes == sizes[0]).all())
+    remote = int(plan.bounds[-1]) - plan.n_local
+    frac = plan.n_halo / remote if remote else 0.0
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor([frac if equal else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item() >= threshold)
+
+
+def dense_columns(plan: HaloPlan) -> np.ndarray:
+    """Column indices for the all-gather data plane: own rows stay local, remote row with
+    global id g is addressed as ``n_local + g`` (the gathered block is in global order)."""
+    col = plan.graph.col_idx.astype(np.int64)
+    remote = col >= plan.n_local
+    out = col.copy()
+    out[remote] = plan.n_local + plan.need_ids[col[remote] - plan.n_local]
+    return out.astype(np.uint32)
+
+
+class Partition:
+    """Device-side state of one rank: plan, device CSR, send indices, buffers.
+
+    Two data planes with identical results: ``sparse`` = pack the rows each peer asked for
+    and exchange them with one all-to-all-v; ``dense`` = copy the whole projected K|V|M
+    block contiguously and all-gather it (chosen collectively when the halo is almost
+    everything, see :func:`choose_dense`)."""
+
+    def __init__(self, plan: HaloPlan, ctx, dense: bool = False):
         import torch
 
-        self.plan, self.ctx = plan, ctx
-        self.graph = plan.graph.to_device(ctx, n_cols=plan.n_local + plan.n_halo)
-        self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
+        from .graph import CsrGraph
+
+        self.plan, self.ctx, self.dense = plan, ctx, dense
+        if dense:
+            n_total = int(plan.bounds[-1])
+            g = CsrGraph(plan.graph.row_ptr, dense_columns(plan), plan.graph.edge_w)
+            self.graph = g.to_device(ctx, n_cols=plan.n_local + n_total)
+            self.send_idx = torch.arange(plan.n_local, dtype=torch.int32, device="cuda")
+        else:
+            self.graph = plan.graph.to_device(ctx, n_cols=plan.n_local + plan.n_halo)
+            self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
         self._send = self._halo = self._x = self._out = None
         self.bytes_exchanged = 0
 
     @classmethod
     def build(cls, local_rows: CsrGraph, rank: int, world: int, n_per_rank: int, ctx) -> "Partition":
-        plan = HaloPlan.build(local_rows, rank, even_bounds(n_per_rank * world, world))
-        return cls(exchange_requests(plan), ctx)
+        plan = exchange_requests(HaloPlan.build(local_rows, rank, even_bounds(n_per_rank * world, world)))
+        return cls(plan, ctx, dense=choose_dense(plan))
 
     def forward(self, layer, x_dev, out_dev, timing: bool = False):
         """project -> pack -> all-to-all-v (NCCL) -> gather/aggregate + update.  Enqueue only."""
@@ -158,9 +200,18 @@ class Partition:
         if n_send:
             _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
                                             C.c_void_p(self._send.data_ptr())))
-        self._halo = exchange_rows(plan, self._send)
-        self.bytes_exchanged = (n_send + plan.n_halo) * 3 * H * 4
-        halo_ptr = self._halo.data_ptr() if plan.n_halo else None
+        if self.dense:
+            import torch.distributed as dist
+
+            n_total = int(plan.bounds[-1])
+            if self._halo is None or self._halo.shape != (n_total, 3 * H):
+                self._halo = torch.empty((n_total, 3 * H), dtype=torch.float32, device=x_dev.device)
+            dist.all_gather_into_tensor(self._halo, self._send)
+            self.bytes_exchanged = (n_total - plan.n_local) * 3 * H * 4 * 2
+        else:
+            self._halo = exchange_rows(plan, self._send)
+            self.bytes_exchanged = (n_send + plan.n_halo) * 3 * H * 4
+        halo_ptr = self._halo.data_ptr() if (plan.n_halo or self.dense) else None
         _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr), 0,
                                                      plan.n_local, C.c_void_p(out_dev.data_ptr())))
 

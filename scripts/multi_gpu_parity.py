@@ -38,7 +38,9 @@ def main():
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         s, e = int(g.row_ptr[lo]), int(g.row_ptr[hi])
         rows = CsrGraph((g.row_ptr[lo:hi + 1] - g.row_ptr[lo]).astype(np.uint64), g.col_idx[s:e].copy(), g.edge_w[s:e].copy())
-        part = rvdist.Partition(rvdist.exchange_requests(rvdist.HaloPlan.build(rows, rank, bounds)), ctx)
+        plan = rvdist.exchange_requests(rvdist.HaloPlan.build(rows, rank, bounds))
+        dense = rvdist.choose_dense(plan)  # locality 0 -> all-gather plane, 0.9 -> all-to-all-v
+        part = rvdist.Partition(plan, ctx, dense=dense)
         xd = torch.from_numpy(x[lo:hi]).cuda()
         od = torch.empty(hi - lo, d, device="cuda")
         part.forward(layer, xd, od)
@@ -58,7 +60,7 @@ def main():
             rel = np.linalg.norm(got - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-6)
             single = layer.forward_graph(x, g.to_device(ctx))
             bit = np.array_equal(single, got)
-            print(f"n={n} d={d} mode={mode} locality={loc}: world={world} halo_rows={part.plan.n_halo} "
+            print(f"n={n} d={d} mode={mode} locality={loc}: world={world} dense={dense} halo_rows={part.plan.n_halo} "
                   f"max_row_rel={rel.max():.2e} bit_identical_to_single_gpu={bit} host_variant_same={same_host}")
             ok = ok and rel.max() <= 1e-4 and bit and same_host
         torch.cuda.set_stream(torch.cuda.default_stream())

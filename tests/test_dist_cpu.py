@@ -81,6 +81,15 @@ def _worker(rank, world, port, n, width, q):
         s, e = int(g.row_ptr[lo]), int(g.row_ptr[hi])
         ok = ok and np.array_equal(full[plan.graph.col_idx], table[g.col_idx[s:e]])
         ok = ok and int(plan.send_counts.sum()) == plan.send_idx.size
+        # dense (all-gather) data plane: remote rows addressed by global id
+        dense = rvdist.choose_dense(plan, threshold=0.0)
+        gathered = [torch.empty_like(local) for _ in range(world)] if (hi - lo) * world == n else None
+        if dense and gathered is not None:
+            dist.all_gather(gathered, local)
+            block = np.concatenate([t.numpy() for t in gathered])
+            full_d = np.concatenate([table[lo:hi], block])
+            ok = ok and np.array_equal(full_d[rvdist.dense_columns(plan)], table[g.col_idx[s:e]])
+        ok = ok and (dense == ((hi - lo) * world == n))  # unequal partitions must fall back
         q.put((rank, bool(ok), plan.n_halo))
     finally:
         dist.destroy_process_group()
