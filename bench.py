@@ -113,9 +113,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def agg_bytes_per_node(H: int, deg_sum: int, n: int) -> float:
-    """Algorithmic bytes of K-agg, formulation R=3 (SURVEY.md 8d / DESIGN.md):
-    per node 4H (Q) + 16 (row_ptr pair) + deg*(4 col + 4 w + 12H) + 8H (o, agg)."""
+def agg_bytes_per_node(H: int, deg_sum: int, n: int, R: int = 3, heads: int = 1) -> float:
+    """Algorithmic bytes of K-agg (SURVEY.md 8d / DESIGN.md).
+    R=3: per node 4H (Q) + 16 (row_ptr pair) + deg*(4 col + 4 w + 12H) + 8H (o, agg).
+    R=1: per node 4hH (folded queries) + 16 + deg*(8 + 4H) + 4(h+1)H (S_0..S_{h-1}, agg)."""
+    if R == 1:
+        return (n * (4 * heads * H + 16 + 4 * (heads + 1) * H) + deg_sum * (8 + 4 * H)) / n
     return (n * (4 * H + 16 + 8 * H) + deg_sum * (8 + 12 * H)) / n
 
 
@@ -335,8 +338,9 @@ def main():
 
     peak, peak_src = measured_peaks()
     agg_ms = float(stage[1]) if stage[1] > 0 else None
-    bytes_launch = agg_bytes_per_node(H, E, n) * n
-    roof = {"kernel": "gather_fast_kernel (K-agg, R=3)", "bound": "hbm",
+    R = int(_lib.load().ruvgnn_layer_halo_width(layer._device_layer())) // H
+    bytes_launch = agg_bytes_per_node(H, E, n, R, a.heads) * n
+    roof = {"kernel": f"{'gather_r1_kernel' if R == 1 else 'gather_fast_kernel'} (K-agg, R={R})", "bound": "hbm",
             "achieved": (bytes_launch / (agg_ms * 1e-3) / 1e9) if agg_ms else None, "peak": peak, "unit": "GB/s",
             "frac": (bytes_launch / (agg_ms * 1e-3) / 1e9 / peak) if agg_ms else None,
             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,

@@ -228,13 +228,16 @@ int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *ctx, const float *queries, uint6
  * that peers need. */
 int32_t ruvgnn_layer_project(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, uint64_t n_local,
                              const float *x_dev);
-/* Gathers rows `idx[0..n_idx)` of the projected K|V|M block into a dense
- * [n_idx][3*hidden_dim] device buffer (the halo send buffer). */
+/* Floats per halo row of this layer: 3*hidden_dim (K|V|M rows) or hidden_dim (message row
+ * only, when the layer runs the single-row gather formulation, hidden_dim == 128). */
+uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *layer);
+/* Gathers rows `idx[0..n_idx)` of the projected block into a dense
+ * [n_idx][ruvgnn_layer_halo_width] device buffer (the halo send buffer). */
 int32_t ruvgnn_halo_pack(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, const uint32_t *idx_dev,
                          uint64_t n_idx, float *send_dev);
 /* Phase B: gather/aggregate + update for local rows [row_begin,row_end).
  * graph col_idx < n_local address own rows, col_idx >= n_local address
- * halo_dev[col - n_local] ([n_halo][3*hidden_dim], received from peers). */
+ * halo_dev[col - n_local] ([n_halo][ruvgnn_layer_halo_width], received from peers). */
 int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
                                       const ruvgnn_graph *graph, const float *halo_dev,
                                       uint64_t row_begin, uint64_t row_end, float *out_dev);

@@ -100,6 +100,28 @@ struct GatherArgs {
 cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
                           uint64_t *launches);
 
+// Single-row (R = 1) formulation, H = 128: per edge only the 512-byte message row M_j is read.
+//   scores  s_gj = (W_k[g]^T q_g) . m_j / sqrt(d_h)   (the q_g . b_k[g] term is constant in j and
+//                                                     cancels in the softmax)
+//   values  o_g  = W_v[g] (sum_j a_gj m_j) + b_v[g]   (sum_j a_gj = 1)
+// so the kernel reads the folded queries Qt [n][heads*H], accumulates S_g = sum_j a_gj m_j per
+// head and writes [S_0 | .. | S_{h-1} | agg]; W_k / W_v are folded into the GEMMs around it.
+struct GatherR1Args {
+  const float *M = nullptr;  // [n_local][ldm] message rows
+  int64_t ldm = 0;
+  const float *halo = nullptr;  // [n_halo][128] remote message rows
+  uint64_t n_local = 0;
+  const float *Qt = nullptr;  // [n_local][heads*128]
+  const uint64_t *row_ptr = nullptr;
+  const uint32_t *col_idx = nullptr;
+  const float *edge_w = nullptr;
+  float *sa = nullptr;  // [n_local][(heads+1)*128]: S_0..S_{h-1} | agg
+  uint64_t row_begin = 0, row_end = 0;
+  uint32_t heads = 0;
+  int prenormalized = 0;
+};
+cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s, uint64_t *launches);
+
 // ---- row ops ----------------------------------------------------------------
 // out[row] = LayerNorm(deg(row) > 0 ? d[row] : m[row]), written in logical order.
 struct LayerNormArgs {

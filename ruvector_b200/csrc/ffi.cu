@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every compute entry needs a CUDA device.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -74,6 +75,10 @@ struct ruvgnn_layer {
   float *Wzr = nullptr, *bzr = nullptr;    // [2H][2H]: rows z|r, cols a|m
   float *Wh = nullptr, *bh = nullptr;      // [H][2H]: cols a|rh
   float *gamma = nullptr, *beta = nullptr;
+  // R = 1 gather formulation (H == 128, heads in {1,2,4,8}; see GatherR1Args): folded weights
+  bool r1 = false;
+  float *Wqk = nullptr, *bqk = nullptr;  // [heads*H][H]: Qt_g = W_k[g]^T (W_q[g] m + b_q[g])
+  float *Wov = nullptr, *bov = nullptr;  // [H][heads*H]: attn = sum_g (W_o[:,g] W_v[g]) S_g + W_o b_v + b_o
   TcWeights tc;  // split (hi/lo) copies for the tcgen05 path; empty unless usable
 };
 
@@ -124,8 +129,12 @@ struct DeviceGuard {
   }
 };
 
-int32_t ensure_ws(ruvgnn_ctx *c, uint64_t n, uint32_t H) {
-  const size_t need = (size_t)n * H * 10 + 64;
+// floats per node of activation workspace: R=3: P(4H) OA(2H) T0..T3(4H); R=1: M(H) Qt(hH)
+// SA((h+1)H) T0..T3(4H)
+uint32_t ws_units(const ruvgnn_layer *L) { return L->r1 ? 2 * L->heads + 6 : 10; }
+
+int32_t ensure_ws(ruvgnn_ctx *c, uint64_t n, uint32_t H, uint32_t units = 10) {
+  const size_t need = (size_t)n * H * units + 64;
   if (need <= c->ws_floats) return RUVGNN_OK;
   if (c->ws) {
     RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -154,13 +163,36 @@ int32_t ensure_stage(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
 struct Ws {
   float *P, *OA, *T0, *T1, *T2, *T3;
   int64_t ldp;
+  // views shared by both formulations
+  float *m;      // message rows (hidden state of the GRU)
+  int64_t ldm;
+  float *halo_src;  // rows a peer needs: K|V|M (3H) or M (H)
+  uint32_t halo_w;
+  // R = 1 only
+  float *Qt, *SA;
 };
-Ws carve(const ruvgnn_ctx *c, uint64_t n, uint32_t H) {
-  Ws w;
-  w.P = c->ws;
-  w.ldp = 4 * (int64_t)H;
-  w.OA = w.P + (size_t)n * 4 * H;
-  w.T0 = w.OA + (size_t)n * 2 * H;
+Ws carve(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
+  const uint32_t H = L->H;
+  Ws w{};
+  if (!L->r1) {
+    w.P = c->ws;
+    w.ldp = 4 * (int64_t)H;
+    w.OA = w.P + (size_t)n * 4 * H;
+    w.T0 = w.OA + (size_t)n * 2 * H;
+    w.m = w.P + 3 * H;
+    w.ldm = w.ldp;
+    w.halo_src = w.P + H;
+    w.halo_w = 3 * H;
+  } else {
+    const uint32_t h = L->heads;
+    w.m = c->ws;
+    w.ldm = H;
+    w.Qt = w.m + (size_t)n * H;
+    w.SA = w.Qt + (size_t)n * h * H;
+    w.T0 = w.SA + (size_t)n * (h + 1) * H;
+    w.halo_src = w.m;
+    w.halo_w = H;
+  }
   w.T1 = w.T0 + (size_t)n * H;
   w.T2 = w.T1 + (size_t)n * H;
   w.T3 = w.T2 + (size_t)n * H;
@@ -185,10 +217,10 @@ int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKin
 int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev,
                         uint64_t rb, uint64_t re) {
   const uint32_t H = L->H, D = L->D;
-  int32_t rc = ensure_ws(c, n, H);
+  int32_t rc = ensure_ws(c, n, H, ws_units(L));
   if (rc) return rc;
   if (re <= rb) return RUVGNN_OK;
-  Ws w = carve(c, n, H);
+  Ws w = carve(c, L, n);
   GemmArgs g;
   g.M = (int64_t)(re - rb);
   g.N = (int32_t)H;
@@ -197,19 +229,27 @@ int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const 
   g.lda1 = D;
   g.W = L->Wmsg;
   g.bias = L->bmsg;
-  g.out = w.P + rb * w.ldp + 3 * H;
-  g.ldo = w.ldp;
+  g.out = w.m + rb * w.ldm;
+  g.ldo = w.ldm;
   if ((rc = run_gemm(c, L, g, EPI_BIAS, TC_W_MSG))) return rc;
   GemmArgs q;
   q.M = (int64_t)(re - rb);
-  q.N = (int32_t)(3 * H);
   q.K1 = (int32_t)H;
-  q.A1 = w.P + rb * w.ldp + 3 * H;
-  q.lda1 = w.ldp;
-  q.W = L->Wqkv;
-  q.bias = L->bqkv;
-  q.out = w.P + rb * w.ldp;
-  q.ldo = w.ldp;
+  q.A1 = w.m + rb * w.ldm;
+  q.lda1 = w.ldm;
+  if (!L->r1) {  // Q | K | V
+    q.N = (int32_t)(3 * H);
+    q.W = L->Wqkv;
+    q.bias = L->bqkv;
+    q.out = w.P + rb * w.ldp;
+    q.ldo = w.ldp;
+  } else {  // folded queries, one H-vector per head
+    q.N = (int32_t)(L->heads * H);
+    q.W = L->Wqk;
+    q.bias = L->bqk;
+    q.out = w.Qt + rb * (size_t)(L->heads * H);
+    q.ldo = (int64_t)L->heads * H;
+  }
   if ((rc = run_gemm(c, L, q, EPI_BIAS, TC_W_QKV))) return rc;
   c->proj_rows = n;
   c->proj_H = H;
@@ -227,34 +267,61 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
   const uint32_t H = L->H;
   const uint64_t n = c->proj_rows;
   if (re <= rb) return RUVGNN_OK;
-  Ws w = carve(c, n, H);
-  GatherArgs ga;
-  ga.P = w.P;
-  ga.ldp = w.ldp;
-  ga.halo = halo;
-  ga.n_local = n;
-  ga.row_ptr = G->row_ptr;
-  ga.col_idx = G->col_idx;
-  ga.edge_w = G->edge_w;
-  ga.oa = w.OA;
-  ga.row_begin = rb;
-  ga.row_end = re;
-  ga.H = H;
-  ga.heads = L->heads;
-  ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+  Ws w = carve(c, L, n);
   if (c->timing_valid && stage_events) cudaEventRecord(c->ev[6], c->stream);
-  RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
+  if (!L->r1) {
+    GatherArgs ga;
+    ga.P = w.P;
+    ga.ldp = w.ldp;
+    ga.halo = halo;
+    ga.n_local = n;
+    ga.row_ptr = G->row_ptr;
+    ga.col_idx = G->col_idx;
+    ga.edge_w = G->edge_w;
+    ga.oa = w.OA;
+    ga.row_begin = rb;
+    ga.row_end = re;
+    ga.H = H;
+    ga.heads = L->heads;
+    ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+    RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
+  } else {
+    GatherR1Args ga;
+    ga.M = w.m;
+    ga.ldm = w.ldm;
+    ga.halo = halo;
+    ga.n_local = n;
+    ga.Qt = w.Qt;
+    ga.row_ptr = G->row_ptr;
+    ga.col_idx = G->col_idx;
+    ga.edge_w = G->edge_w;
+    ga.sa = w.SA;
+    ga.row_begin = rb;
+    ga.row_end = re;
+    ga.heads = L->heads;
+    ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+    RUVGNN_CUDA_TRY(launch_gather_r1(ga, c->sm_count, c->stream, &c->launches));
+  }
   if (c->timing_valid && stage_events) cudaEventRecord(c->ev[3], c->stream);
 
   const int64_t rows = (int64_t)(re - rb);
-  const float *m = w.P + rb * w.ldp + 3 * H;
+  const float *m = w.m + rb * w.ldm;
   int32_t rc;
-  {  // combined = W_o o + b_o + agg
+  if (!L->r1) {  // combined = W_o o + b_o + agg
     GemmArgs g;
     g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H;
     g.A1 = w.OA + rb * 2 * H; g.lda1 = 2 * H;
     g.W = L->Wo; g.bias = L->bo;
     g.add = w.OA + rb * 2 * H + H; g.ldadd = 2 * H;
+    g.out = w.T0 + rb * H; g.ldo = H;
+    if ((rc = run_gemm(c, L, g, EPI_BIAS_ADD, TC_W_O))) return rc;
+  } else {  // combined = sum_g (W_o[:,g] W_v[g]) S_g + (W_o b_v + b_o) + agg
+    const int64_t ld = (int64_t)(L->heads + 1) * H;
+    GemmArgs g;
+    g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)(L->heads * H);
+    g.A1 = w.SA + rb * ld; g.lda1 = ld;
+    g.W = L->Wov; g.bias = L->bov;
+    g.add = w.SA + rb * ld + (size_t)L->heads * H; g.ldadd = ld;
     g.out = w.T0 + rb * H; g.ldo = H;
     if ((rc = run_gemm(c, L, g, EPI_BIAS_ADD, TC_W_O))) return rc;
   }
@@ -270,9 +337,9 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
     GemmArgs g;
     g.M = rows; g.N = (int32_t)(2 * H); g.K1 = (int32_t)H; g.K2 = (int32_t)H;
     g.A1 = w.T1 + rb * H; g.lda1 = H;
-    g.A2 = m; g.lda2 = w.ldp;
+    g.A2 = m; g.lda2 = w.ldm;
     g.W = L->Wzr; g.bias = L->bzr;
-    g.m = m; g.ldm = w.ldp;
+    g.m = m; g.ldm = w.ldm;
     g.z = w.T2 + rb * H; g.ldz = H;
     g.rh = w.T3 + rb * H; g.ldrh = H;
     g.H = (int32_t)H;
@@ -284,7 +351,7 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
     g.A1 = w.T1 + rb * H; g.lda1 = H;
     g.A2 = w.T3 + rb * H; g.lda2 = H;
     g.W = L->Wh; g.bias = L->bh;
-    g.m = m; g.ldm = w.ldp;
+    g.m = m; g.ldm = w.ldm;
     g.z = w.T2 + rb * H; g.ldz = H;
     g.out = w.T0 + rb * H; g.ldo = H;
     g.H = (int32_t)H;
@@ -293,7 +360,7 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
   }
   LayerNormArgs ln;
   ln.d = w.T0; ln.ldd = H;
-  ln.m = w.P + 3 * H; ln.ldm = w.ldp;
+  ln.m = w.m; ln.ldm = w.ldm;
   ln.row_ptr = G->row_ptr;
   ln.gamma = L->gamma; ln.beta = L->beta; ln.eps = L->host.eps;
   ln.out = out_dev;
@@ -314,7 +381,9 @@ int32_t upload_layer(ruvgnn_layer *L) {
   const size_t nW = (size_t)H * D + 3 * (size_t)H * H + 2 * (size_t)H * H + 4 * (size_t)H * H +
                     2 * (size_t)H * H;
   const size_t nB = (size_t)H + 3 * H + H + H + 2 * H + H + 2 * H;
-  std::vector<float> blob(nW + nB + 64, 0.f);
+  // + room for the R = 1 folded matrices (2 * heads * H * H + biases), allocated when used
+  const size_t nR1 = (H == 128 && L->heads <= 8) ? 2 * (size_t)L->heads * H * H + (size_t)L->heads * H + H + 16 : 0;
+  std::vector<float> blob(nW + nB + nR1 + 64, 0.f);
   size_t off = 0;
   auto take = [&](size_t n) {
     float *p = blob.data() + off;
@@ -328,6 +397,11 @@ int32_t upload_layer(ruvgnn_layer *L) {
   float *Wzr = take(4 * (size_t)H * H), *bzr = take(2 * H);
   float *Wh = take(2 * (size_t)H * H), *bh = take(H);
   float *gamma = take(H), *beta = take(H);
+  {
+    const char *e = getenv("RUVGNN_R1");
+    const uint32_t hh = L->heads;
+    L->r1 = L->fast && H == 128 && (hh == 1 || hh == 2 || hh == 4 || hh == 8) && !(e && atoi(e) == 0);
+  }
   // rows_perm / cols_perm: does the output / input of this Linear live in phys order?
   auto place = [&](const HostLinear &l, float *W, size_t ldw, size_t row_off, size_t col_off,
                    bool cols_perm) {
@@ -376,6 +450,47 @@ int32_t upload_layer(ruvgnn_layer *L) {
     gamma[ord.phys(i)] = h.gamma[i];
     beta[ord.phys(i)] = h.beta[i];
   }
+  float *Wqk = nullptr, *bqk = nullptr, *Wov = nullptr, *bov = nullptr;
+  if (L->r1) {
+    // P == 1, so the column order is the identity.  Products are formed in double precision.
+    const uint32_t hh = L->heads, dh = H / hh;
+    Wqk = take((size_t)hh * H * H);
+    bqk = take((size_t)hh * H);
+    Wov = take((size_t)hh * H * H);
+    bov = take(H);
+    const HostLinear &lq = h.lin[L_Q], &lk = h.lin[L_K], &lv = h.lin[L_V], &lo = h.lin[L_OUT];
+    for (uint32_t g = 0; g < hh; ++g)
+      for (uint32_t cidx = 0; cidx < H; ++cidx) {
+        // Qt_g[c] = sum_{t in head g} W_k[t][c] * (W_q[t] . m + b_q[t])
+        float *row = Wqk + ((size_t)g * H + cidx) * H;
+        double bsum = 0.0;
+        std::vector<double> acc(H, 0.0);
+        for (uint32_t t = g * dh; t < (g + 1) * dh; ++t) {
+          const double wk = lk.w[(size_t)t * H + cidx];
+          const float *wq = lq.w.data() + (size_t)t * H;
+          for (uint32_t i = 0; i < H; ++i) acc[i] += wk * (double)wq[i];
+          bsum += wk * (double)lq.b[t];
+        }
+        for (uint32_t i = 0; i < H; ++i) row[i] = (float)acc[i];
+        bqk[(size_t)g * H + cidx] = (float)bsum;
+      }
+    for (uint32_t o = 0; o < H; ++o) {
+      // attn[o] = sum_g sum_c (sum_{t in head g} W_o[o][t] W_v[t][c]) S_g[c] + sum_t W_o[o][t] b_v[t] + b_o[o]
+      float *row = Wov + (size_t)o * hh * H;
+      double bsum = (double)lo.b[o];
+      for (uint32_t g = 0; g < hh; ++g) {
+        std::vector<double> acc(H, 0.0);
+        for (uint32_t t = g * dh; t < (g + 1) * dh; ++t) {
+          const double wo = lo.w[(size_t)o * H + t];
+          const float *wv = lv.w.data() + (size_t)t * H;
+          for (uint32_t i = 0; i < H; ++i) acc[i] += wo * (double)wv[i];
+          bsum += wo * (double)lv.b[t];
+        }
+        for (uint32_t i = 0; i < H; ++i) row[(size_t)g * H + i] = (float)acc[i];
+      }
+      bov[o] = (float)bsum;
+    }
+  }
   RUVGNN_CUDA_TRY(cudaMalloc(&L->blob, blob.size() * sizeof(float)));
   RUVGNN_CUDA_TRY(
       cudaMemcpy(L->blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -387,10 +502,14 @@ int32_t upload_layer(ruvgnn_layer *L) {
   L->Wzr = dev(Wzr); L->bzr = dev(bzr);
   L->Wh = dev(Wh); L->bh = dev(bh);
   L->gamma = dev(gamma); L->beta = dev(beta);
+  if (L->r1) {
+    L->Wqk = dev(Wqk); L->bqk = dev(bqk);
+    L->Wov = dev(Wov); L->bov = dev(bov);
+  }
   // tcgen05 path: split copies (hi/lo) of the six device weight matrices
-  const float *mats[TC_W_COUNT] = {Wmsg, Wqkv, Wo, Wagg, Wzr, Wh};
-  const uint32_t rows[TC_W_COUNT] = {H, 3 * H, H, H, 2 * H, H};
-  const uint32_t cols[TC_W_COUNT] = {D, H, H, H, 2 * H, 2 * H};
+  const float *mats[TC_W_COUNT] = {Wmsg, L->r1 ? Wqk : Wqkv, L->r1 ? Wov : Wo, Wagg, Wzr, Wh};
+  const uint32_t rows[TC_W_COUNT] = {H, L->r1 ? L->heads * H : 3 * H, H, H, 2 * H, H};
+  const uint32_t cols[TC_W_COUNT] = {D, H, L->r1 ? L->heads * H : H, H, 2 * H, 2 * H};
   cudaError_t e = tc_weights_create(mats, rows, cols, &L->tc);
   if (e != cudaSuccess)
     return fail(RUVGNN_ERR_CUDA, std::string("tc_weights_create: ") + cudaGetErrorString(e));
@@ -751,7 +870,7 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   } else if (x == out) {
     return fail(RUVGNN_ERR_INVALID_INPUT, "out must not alias x (Jacobi update)");
   }
-  if ((rc = ensure_ws(c, n, L->H))) return rc;
+  if ((rc = ensure_ws(c, n, L->H, ws_units(L)))) return rc;
   if (timing) {
     c->timing_valid = true;
     c->ev = c->ring[c->ring_count % ruvgnn_ctx::kRing];
@@ -846,7 +965,9 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
   int32_t rc;
   uint32_t maxH = 0;
   for (uint32_t l = 0; l < n_layers; ++l) maxH = layers[l]->H > maxH ? layers[l]->H : maxH;
-  if ((rc = ensure_ws(c, n, maxH))) return rc;
+  uint32_t max_units = 10;
+  for (uint32_t l = 0; l < n_layers; ++l) max_units = ws_units(layers[l]) > max_units ? ws_units(layers[l]) : max_units;
+  if ((rc = ensure_ws(c, n, maxH, max_units))) return rc;
   const float *cur = x;
   if (!dev_ptrs) {
     if ((rc = ensure_stage(c, &c->x_stage, &c->x_stage_floats, (size_t)n * layers[0]->D))) return rc;
@@ -938,6 +1059,11 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   return rc;
 }
 
+uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *L) {
+  if (!L) return 0;
+  return L->r1 ? L->H : 3 * L->H;
+}
+
 int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *idx_dev,
                          uint64_t n_idx, float *send_dev) {
   if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
@@ -946,8 +1072,8 @@ int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *i
   if (c->proj_rows == 0 || c->proj_H != L->H)
     return fail(RUVGNN_ERR_INVALID_INPUT, "ruvgnn_layer_project has not run for this layer");
   DeviceGuard dg(c->device);
-  Ws w = carve(c, c->proj_rows, L->H);
-  RUVGNN_CUDA_TRY(launch_pack_rows(w.P + L->H, w.ldp, 3 * L->H, idx_dev, n_idx, send_dev,
+  Ws w = carve(c, L, c->proj_rows);
+  RUVGNN_CUDA_TRY(launch_pack_rows(w.halo_src, w.ldm, w.halo_w, idx_dev, n_idx, send_dev,
                                    c->stream, &c->launches));
   return RUVGNN_OK;
 }

@@ -228,6 +228,145 @@ __global__ void gather_generic_kernel(GatherArgs a, float inv_scale) {
   }
 }
 
+
+// ---- R = 1 kernel (H = 128) --------------------------------------------------------------
+// Sum each of the N per-lane partials over the 32 lanes and leave ALL N totals in every lane.
+// Halving butterfly: each xor step exchanges half of the remaining values, so N totals cost
+// (N-1) + (5 - log2 N) + N shuffles instead of 5N.
+template <int N>
+__device__ __forceinline__ void reduce_all(float (&v)[N], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = up ? v[i + n / 2] : v[i];
+      const float send = up ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  // lane L now holds the total of value index id(L) = bits of L at the halving offsets
+  const float mine = v[0];
+#pragma unroll
+  for (int g = 0; g < N; ++g) {
+    int src = 0, o = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+      if (g & (n / 2)) src |= o;
+      o >>= 1;
+    }
+    v[g] = __shfl_sync(0xffffffffu, mine, src);
+  }
+}
+
+template <int HEADS, int U>
+__global__ void __launch_bounds__(128) gather_r1_kernel(GatherR1Args a, float scale_log2) {
+  constexpr int H = 128;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
+    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    float4 *srow = reinterpret_cast<float4 *>(a.sa + node * (uint64_t)((HEADS + 1) * H));
+    if (beg == end) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g <= HEADS; ++g) srow[g * 32 + lane] = zero;
+      continue;
+    }
+    const float4 *qrow = reinterpret_cast<const float4 *>(a.Qt + node * (uint64_t)(HEADS * H));
+    float4 qt[HEADS], S[HEADS];
+    float mx[HEADS], l[HEADS];
+#pragma unroll
+    for (int g = 0; g < HEADS; ++g) {
+      const float4 q = ldg4(qrow + g * 32 + lane);
+      // scores are taken in log2 units: exp(s - m) == exp2(s' - m') with s' = s * log2(e)
+      qt[g] = make_float4(q.x * scale_log2, q.y * scale_log2, q.z * scale_log2, q.w * scale_log2);
+      S[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mx[g] = -INFINITY;
+      l[g] = 0.f;
+    }
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f);
+    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
+    auto row_of = [&](uint32_t col) -> const float4 * {
+      return (uint64_t)col < a.n_local
+                 ? reinterpret_cast<const float4 *>(a.M + (uint64_t)col * a.ldm)
+                 : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * H);
+    };
+    auto consume = [&](const float4 m, float what) {
+      float s[HEADS];
+#pragma unroll
+      for (int g = 0; g < HEADS; ++g)
+        s[g] = fmaf(qt[g].x, m.x, fmaf(qt[g].y, m.y, fmaf(qt[g].z, m.z, qt[g].w * m.w)));
+      reduce_all<HEADS>(s, lane);
+#pragma unroll
+      for (int g = 0; g < HEADS; ++g) {
+        if (s[g] > mx[g]) {  // warp-uniform: every lane holds the same totals
+          const float corr = exp2f(mx[g] - s[g]);
+          l[g] *= corr;
+          S[g].x *= corr; S[g].y *= corr; S[g].z *= corr; S[g].w *= corr;
+          mx[g] = s[g];
+        }
+        const float p = exp2f(s[g] - mx[g]);
+        l[g] += p;
+        S[g].x = fmaf(p, m.x, S[g].x);
+        S[g].y = fmaf(p, m.y, S[g].y);
+        S[g].z = fmaf(p, m.z, S[g].z);
+        S[g].w = fmaf(p, m.w, S[g].w);
+      }
+      ag.x = fmaf(what, m.x, ag.x);
+      ag.y = fmaf(what, m.y, ag.y);
+      ag.z = fmaf(what, m.z, ag.z);
+      ag.w = fmaf(what, m.w, ag.w);
+    };
+    for (uint64_t c = beg; c < end; c += 32) {
+      const uint64_t e = c + lane;
+      const uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      const float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
+      const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
+      int jj = 0;
+      for (; jj + U <= cnt; jj += U) {
+        float4 r[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t col = __shfl_sync(0xffffffffu, my_col, jj + u);
+          w[u] = __shfl_sync(0xffffffffu, my_w, jj + u);
+          r[u] = ldg4(row_of(col) + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(r[u], w[u]);
+      }
+      for (; jj < cnt; ++jj) {
+        const uint32_t col = __shfl_sync(0xffffffffu, my_col, jj);
+        const float w = __shfl_sync(0xffffffffu, my_w, jj);
+        consume(ldg4(row_of(col) + lane), w);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < HEADS; ++g) {
+      const float inv_l = 1.0f / fmaxf(l[g], 1e-10f);
+      srow[g * 32 + lane] = make_float4(S[g].x * inv_l, S[g].y * inv_l, S[g].z * inv_l, S[g].w * inv_l);
+    }
+    srow[HEADS * 32 + lane] = ag;
+  }
+}
+
+template <int HEADS>
+cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, cudaStream_t s) {
+  const uint64_t rows = a.row_end - a.row_begin;
+  const int wpb = 4;
+  uint64_t blocks = (rows + wpb - 1) / wpb;
+  const uint64_t cap = (uint64_t)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  gather_r1_kernel<HEADS, 4><<<(unsigned)blocks, 32 * wpb, 0, s>>>(a, scale_log2);
+  return cudaGetLastError();
+}
+
 template <int P, int U>
 cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cudaStream_t s) {
   const uint64_t rows = a.row_end - a.row_begin;
@@ -251,6 +390,20 @@ cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cu
 }
 
 }  // namespace
+
+cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s,
+                             uint64_t *launches) {
+  if (a.row_end <= a.row_begin) return cudaSuccess;
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)(128 / a.heads));
+  if (launches) ++*launches;
+  switch (a.heads) {
+    case 1: return launch_r1_h<1>(a, scale_log2, sm_count, s);
+    case 2: return launch_r1_h<2>(a, scale_log2, sm_count, s);
+    case 4: return launch_r1_h<4>(a, scale_log2, sm_count, s);
+    case 8: return launch_r1_h<8>(a, scale_log2, sm_count, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
 
 cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
                           uint64_t *launches) {

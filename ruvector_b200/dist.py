@@ -195,8 +195,9 @@ class Partition:
         h = layer._device_layer()
         _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, plan.n_local, C.c_void_p(x_dev.data_ptr())))
         n_send = int(self.send_idx.numel())
-        if self._send is None or self._send.shape != (n_send, 3 * H):
-            self._send = torch.empty((n_send, 3 * H), dtype=torch.float32, device=x_dev.device)
+        W = int(lib.ruvgnn_layer_halo_width(h))  # 3H (K|V|M rows) or H (message rows, R=1 layers)
+        if self._send is None or self._send.shape != (n_send, W):
+            self._send = torch.empty((n_send, W), dtype=torch.float32, device=x_dev.device)
         if n_send:
             _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
                                             C.c_void_p(self._send.data_ptr())))
@@ -204,13 +205,13 @@ class Partition:
             import torch.distributed as dist
 
             n_total = int(plan.bounds[-1])
-            if self._halo is None or self._halo.shape != (n_total, 3 * H):
-                self._halo = torch.empty((n_total, 3 * H), dtype=torch.float32, device=x_dev.device)
+            if self._halo is None or self._halo.shape != (n_total, W):
+                self._halo = torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
             dist.all_gather_into_tensor(self._halo, self._send)
-            self.bytes_exchanged = (n_total - plan.n_local) * 3 * H * 4 * 2
+            self.bytes_exchanged = (n_total - plan.n_local) * W * 4 * 2
         else:
             self._halo = exchange_rows(plan, self._send)
-            self.bytes_exchanged = (n_send + plan.n_halo) * 3 * H * 4
+            self.bytes_exchanged = (n_send + plan.n_halo) * W * 4
         halo_ptr = self._halo.data_ptr() if (plan.n_halo or self.dense) else None
         _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr), 0,
                                                      plan.n_local, C.c_void_p(out_dev.data_ptr())))
