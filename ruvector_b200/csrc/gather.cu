@@ -230,6 +230,12 @@ __global__ void gather_generic_kernel(GatherArgs a, float inv_scale) {
 
 
 // ---- R = 1 kernel (H = 128) --------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {  // 2^x, x <= 0 here; flushes to 0 below 2^-126
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Sum each of the N per-lane partials over the 32 lanes and leave ALL N totals in every lane.
 // Halving butterfly: each xor step exchanges half of the remaining values, so N totals cost
 // (N-1) + (5 - log2 N) + N shuffles instead of 5N.
@@ -305,18 +311,19 @@ __global__ void __launch_bounds__(128) gather_r1_kernel(GatherR1Args a, float sc
       reduce_all<HEADS>(s, lane);
 #pragma unroll
       for (int g = 0; g < HEADS; ++g) {
-        if (s[g] > mx[g]) {  // warp-uniform: every lane holds the same totals
-          const float corr = exp2f(mx[g] - s[g]);
-          l[g] *= corr;
-          S[g].x *= corr; S[g].y *= corr; S[g].z *= corr; S[g].w *= corr;
-          mx[g] = s[g];
-        }
-        const float p = exp2f(s[g] - mx[g]);
-        l[g] += p;
-        S[g].x = fmaf(p, m.x, S[g].x);
-        S[g].y = fmaf(p, m.y, S[g].y);
-        S[g].z = fmaf(p, m.z, S[g].z);
-        S[g].w = fmaf(p, m.w, S[g].w);
+        // Branch-free online softmax with ONE exp2 per head: with d = s - mx, either the new
+        // score is the maximum (p = 1, corr = 2^-d) or the old one stays (corr = 1, p = 2^d).
+        const float d = s[g] - mx[g];
+        const float e = ex2_approx(-fabsf(d));  // mx = -inf on the first edge: d = +inf, e = 0
+        const bool grow = d > 0.f;
+        const float corr = grow ? e : 1.0f;
+        const float p = grow ? 1.0f : e;
+        mx[g] = fmaxf(mx[g], s[g]);
+        l[g] = fmaf(l[g], corr, p);
+        S[g].x = fmaf(S[g].x, corr, p * m.x);
+        S[g].y = fmaf(S[g].y, corr, p * m.y);
+        S[g].z = fmaf(S[g].z, corr, p * m.z);
+        S[g].w = fmaf(S[g].w, corr, p * m.w);
       }
       ag.x = fmaf(what, m.x, ag.x);
       ag.y = fmaf(what, m.y, ag.y);
@@ -363,7 +370,7 @@ cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, c
   uint64_t blocks = (rows + wpb - 1) / wpb;
   const uint64_t cap = (uint64_t)sm_count * 16;
   if (blocks > cap) blocks = cap;
-  gather_r1_kernel<HEADS, 4><<<(unsigned)blocks, 32 * wpb, 0, s>>>(a, scale_log2);
+  gather_r1_kernel<HEADS, (HEADS <= 4 ? 8 : 4)><<<(unsigned)blocks, 32 * wpb, 0, s>>>(a, scale_log2);
   return cudaGetLastError();
 }
 
