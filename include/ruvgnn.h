@@ -229,7 +229,7 @@ int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *ctx, const float *queries, uint6
 int32_t ruvgnn_layer_project(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, uint64_t n_local,
                              const float *x_dev);
 /* Floats per halo row of this layer: 3*hidden_dim (K|V|M rows) or hidden_dim (message row
- * only, when the layer runs the single-row gather formulation, hidden_dim == 128). */
+ * only, when the layer runs the single-row gather formulation: hidden_dim == 128, <= 4 heads). */
 uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *layer);
 /* Gathers rows `idx[0..n_idx)` of the projected block into a dense
  * [n_idx][ruvgnn_layer_halo_width] device buffer (the halo send buffer). */

@@ -400,7 +400,12 @@ int32_t upload_layer(ruvgnn_layer *L) {
   {
     const char *e = getenv("RUVGNN_R1");
     const uint32_t hh = L->heads;
-    L->r1 = L->fast && H == 128 && (hh == 1 || hh == 2 || hh == 4 || hh == 8) && !(e && atoi(e) == 0);
+    // measured on B200 (1M nodes, deg ~48): R=1 wins for <= 4 heads (K-agg 8.7 vs 13.2 ms at 4
+    // heads); at 8 heads the per-edge work (8 full-width dots + updates) makes it slower (25.6 ms),
+    // so 8 heads stays on the R=3 kernel unless RUVGNN_R1=2 forces it.
+    const int want = e ? atoi(e) : 1;
+    L->r1 = L->fast && H == 128 && want != 0 &&
+            (hh == 1 || hh == 2 || hh == 4 || (hh == 8 && want == 2));
   }
   // rows_perm / cols_perm: does the output / input of this Linear live in phys order?
   auto place = [&](const HostLinear &l, float *W, size_t ldw, size_t row_off, size_t col_off,
