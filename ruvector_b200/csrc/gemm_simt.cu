@@ -16,10 +16,13 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
 
-__device__ __forceinline__ float sigmoid_ref(float x) {  // layer.rs:278-285
-  if (x > 0.f) return 1.0f / (1.0f + expf(-x));
-  const float ex = expf(x);
-  return ex / (1.0f + ex);
+__device__ __forceinline__ float sigmoid_ref(float x) {
+  // GRUCell::sigmoid (layer.rs:278-285): x > 0 ? 1/(1+exp(-x)) : exp(x)/(1+exp(x)).  Both
+  // branches use exp(-|x|); written branch-free with one exp and one divide (the x <= 0 case
+  // multiplies by the reciprocal instead of dividing: <= 1 ulp).
+  const float t = expf(-fabsf(x));
+  const float r = 1.0f / (1.0f + t);
+  return x > 0.f ? r : t * r;
 }
 
 template <int EPI>
