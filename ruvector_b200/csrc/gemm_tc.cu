@@ -309,7 +309,13 @@ EncodeTiledFn get_encode() {
 }
 
 int pick_block_n(uint32_t n) {
-  for (int bn = 256; bn >= 32; bn -= 32)  // epilogue walks 32-column chunks
+  static int cap = 0;  // RUVGNN_TC_BN_MAX: experiments with narrower column tiles
+  if (!cap) {
+    const char *e = getenv("RUVGNN_TC_BN_MAX");
+    cap = e ? atoi(e) : 256;
+    if (cap < 32 || cap > 256) cap = 256;
+  }
+  for (int bn = cap - cap % 32; bn >= 32; bn -= 32)  // epilogue walks 32-column chunks
     if (n % bn == 0) return bn;
   return 0;
 }
