@@ -56,7 +56,7 @@ def full(rep, dst, js=None):
                 if h in KEYS:
                     w.writerow([name, h, u, v])
                     vals[h] = (v, u)
-            if js:
+            if js and json.loads(js).get("kernel", "").split("<")[0] in name:
                 rd, wr = vals.get("dram__bytes_read.sum"), vals.get("dram__bytes_write.sum")
                 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}
                 tot = float(rd[0].replace(",", "")) * scale[rd[1]] + float(wr[0].replace(",", "")) * scale[wr[1]]
