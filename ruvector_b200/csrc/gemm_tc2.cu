@@ -12,6 +12,8 @@
 //   full_b[s]   leader's, 1 arrival (leader's expect_tx) + TMA bytes from BOTH CTAs
 //   empty[s]    each CTA's own, signalled by tcgen05.commit ... multicast::cluster
 //   tmem_full   each CTA's own, multicast commit;  tmem_empty: leader's, 8 epilogue warps
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ruvgnn {
@@ -143,12 +145,16 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
         const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * HN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (leader) {
-            const uint32_t bytes = (p.single_pass ? 1u : 2u) * 2u * (uint32_t)b_tile_bytes;
-            mbar_arrive_expect_tx(&full_b[stage], bytes);
+          if (p.debug & 2) {
+            if (leader) mbar_arrive(&full_b[stage]);
+          } else {
+            if (leader) {
+              const uint32_t bytes = (p.single_pass ? 1u : 2u) * 2u * (uint32_t)b_tile_bytes;
+              mbar_arrive_expect_tx(&full_b[stage], bytes);
+            }
+            tma_load_2d_pair(b_hi(stage), &map_hi, &full_b[stage], kb * BK, n0);
+            if (!p.single_pass) tma_load_2d_pair(b_lo(stage), &map_lo, &full_b[stage], kb * BK, n0);
           }
-          tma_load_2d_pair(b_hi(stage), &map_hi, &full_b[stage], kb * BK, n0);
-          if (!p.single_pass) tma_load_2d_pair(b_lo(stage), &map_lo, &full_b[stage], kb * BK, n0);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -180,7 +186,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t off = (uint64_t)((kk * 32) >> 4);
             const uint32_t first = (kb | kk) ? 1u : 0u;
-            if (p.single_pass) {
+            if (p.debug & 4) {
+            } else if (p.single_pass) {
               umma_tf32_pair(d, ah + off, bh + off, idesc, first);
             } else {
               umma_tf32_pair(d, al + off, bh + off, idesc, first);
@@ -229,7 +236,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
       }
     };
     int tile = pair, kb = 0;
-    if (tile < num_tiles) issue(nxt, tile, 0);
+    if (tile < num_tiles && !(p.debug & 1)) issue(nxt, tile, 0);
+    if (p.debug & 1)
+      for (int i = 0; i < CH; ++i) nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     while (tile < num_tiles) {
 #pragma unroll
       for (int i = 0; i < CH; ++i) cur[i] = nxt[i];
@@ -238,11 +247,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
         nkb = 0;
         ntile = tile + num_pairs;
       }
-      if (ntile < num_tiles) issue(nxt, ntile, nkb);
+      if (ntile < num_tiles && !(p.debug & 1)) issue(nxt, ntile, nkb);
       mbar_wait(&empty[stage], phase ^ 1);
       uint8_t *hi = a_hi(stage), *lo = a_lo(stage);
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
+        if (p.debug & 1) break;
         const uint32_t off = swz_off<BK>(i * RPP + rsub, chunk);
         float4 h;
         h.x = __uint_as_float((__float_as_uint(cur[i].x) + 0x1000u) & 0xFFFFE000u);
@@ -286,7 +296,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
       for (int c = 0; c < BN; c += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        if (row0 >= g.M) continue;
+        if (row0 >= g.M || (p.debug & 8)) continue;
         if (COAL) {
           epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
         } else if (row < g.M) {
@@ -340,7 +350,14 @@ cudaError_t launch_gemm_tc_pair(const GemmArgs &g, EpiKind epi, const TcMaps &ma
   p.g = g;
   p.block_n = maps.block_n[which];
   p.single_pass = single_pass ? 1 : 0;
-  p.debug = 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char *e = getenv("RUVGNN_TC_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   p.num_m_tiles = (int)((g.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
   p.num_n_tiles = g.N / p.block_n;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)(p.block_n / 2) * BK * 4;

@@ -299,3 +299,26 @@ def test_nine_million_nodes_64bit_offsets_sampled_against_oracle(oracle, ctx):
         ref = oracle.forward_node(layer, x[i], x[col[s:t]], w[s:t])
         rel = np.linalg.norm(out[i] - ref) / max(np.linalg.norm(ref), 1e-6)
         assert rel <= 1e-4, (int(i), rel)
+
+
+def test_config2_full_size_sampled_against_oracle(oracle, ctx):
+    """BASELINE config 2 at full size (the bench workload): 1M nodes, d=384, HNSW M=32
+    (level-0 degree U{32..64}), 8 heads, tcgen05 3xTF32 projections.  Rows sampled uniformly,
+    plus the first/last rows and isolated rows, are checked against the oracle's per-node
+    forward (the reference's own call pattern)."""
+    n, d, heads, m = 1_000_000, 384, 8, 32
+    x = synth.make_features(n, d)
+    g = synth.hnsw_like_graph(n, m)
+    layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d), ctx=ctx, mode=rv.MODE_FP32_TC)
+    out = layer.forward_graph(x, g.to_device(ctx))
+    assert np.isfinite(out[::101]).all()
+    deg = g.degrees()
+    rng = np.random.default_rng(5)
+    sample = np.concatenate([rng.integers(0, n, size=40), np.arange(4), np.arange(n - 4, n),
+                             np.nonzero(deg == 0)[0][:3], [int(np.argmax(deg))]])
+    worst = 0.0
+    for i in sample:
+        s, t = int(g.row_ptr[i]), int(g.row_ptr[i + 1])
+        ref = oracle.forward_node(layer, x[i], x[g.col_idx[s:t]], g.edge_w[s:t])
+        worst = max(worst, float(np.linalg.norm(out[i] - ref) / max(np.linalg.norm(ref), 1e-6)))
+    assert worst <= 1e-4, worst
