@@ -454,6 +454,21 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       maps->pair_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
     }
+    // A-in-TMEM kernel: column tiles of at most 192 so two A stages fit beside the accumulators
+    maps->ts_ok[i] = false;
+    maps->block_n3[i] = pick_block_n_ts(rows[i]);
+    if (maps->block_n3[i] > 0) {
+      const cuuint32_t box3[2] = {32u, (cuuint32_t)maps->block_n3[i]};
+      CUresult r1 = encode(&maps->hi3[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->hi[i], dims,
+                           strides, box3, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r2 = encode(&maps->lo3[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->lo[i], dims,
+                           strides, box3, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      maps->ts_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+    }
   }
   out->tmaps = maps;
   out->usable = true;
@@ -476,6 +491,17 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
   if ((uint32_t)g.N != w.rows[which] || (uint32_t)(g.K1 + g.K2) != w.cols[which] ||
       g.K1 % 32 != 0 || g.K2 % 32 != 0)
     return cudaErrorInvalidValue;
+  {
+    static int ts = -1;  // RUVGNN_TC_TS=1: A operand from TMEM (gemm_tc3.cu)
+    if (ts < 0) {
+      const char *e = getenv("RUVGNN_TC_TS");
+      ts = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (ts && maps->ts_ok[which]) {
+      if (launches) ++*launches;
+      return launch_gemm_tc_ts(g, epi, *maps, which, single_pass, sm_count, s);
+    }
+  }
   if (tc_pair_enabled() && maps->pair_ok[which] && sm_count >= 2) {
     if (launches) ++*launches;
     return launch_gemm_tc_pair(g, epi, *maps, which, single_pass, sm_count, s);
