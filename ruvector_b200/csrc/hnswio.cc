@@ -126,6 +126,7 @@ int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out) {
   for (uint32_t b = 0; b < blocks; ++b) {
     if (r.get<uint32_t>() != MAGICLAYER || !r.ok) return bad("bad magic at layer beginning");
     const uint64_t npts = r.get<uint64_t>();
+    if (!r.ok || npts > (uint64_t)(r.end - r.p) / 12) return bad("implausible point count in layer");
     for (uint64_t j = 0; j < npts; ++j) {
       if (r.get<uint32_t>() != MAGICPOINT || !r.ok) return bad("bad magic at point beginning");
       const uint64_t origin = r.get<uint64_t>();
@@ -140,7 +141,7 @@ int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out) {
       for (uint32_t l = 0; l < L; ++l) {
         const uint64_t cnt = r.get<uint64_t>();
         const size_t rec = 8 + (full ? 5 : 0) + 4;
-        if (!r.ok || (uint64_t)(r.end - r.p) < cnt * rec) return bad("truncated neighbour list");
+        if (!r.ok || cnt > (uint64_t)(r.end - r.p) / rec) return bad("truncated neighbour list");
         for (uint64_t k = 0; k < cnt; ++k) {
           d->ids.push_back(r.get<uint64_t>());
           if (full) r.skip(5);

@@ -78,6 +78,16 @@ def test_corrupt_dumps_are_rejected(tmp_path, built):
         HnswDump(bad)
     with pytest.raises(rv.InvalidInput):
         HnswDump(tmp_path / "missing.hnsw.graph")
+    # an absurd neighbour count (first list of the first point) must be rejected, not allocated
+    import struct
+    hdr = 4 + 1 + 1 + 8 + 1 + 8 * 3 + 8 + len("DistCosine") + 8 + len("f32")  # Description (v4)
+    pos = hdr + 1 + 4 + 8 + 4 + 8 + 5  # nb_layer, MAGICLAYER, nb_point, MAGICPOINT, origin_id, p_id
+    huge = bytearray(raw)
+    huge[pos:pos + 8] = struct.pack("=Q", 1 << 61)
+    bad.write_bytes(bytes(huge))
+    with pytest.raises(rv.InvalidInput) as e:
+        HnswDump(bad)
+    assert "truncated neighbour list" in str(e.value)
     empty = tmp_path / "empty.hnsw.graph"
     write_graph_dump(empty, [])
     d = HnswDump(empty)
