@@ -492,12 +492,18 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
       g.K1 % 32 != 0 || g.K2 % 32 != 0)
     return cudaErrorInvalidValue;
   {
-    static int ts = -1;  // RUVGNN_TC_TS=1: A operand from TMEM (gemm_tc3.cu)
-    if (ts < 0) {
+    // A operand from TMEM (gemm_tc3.cu) vs from shared memory (this file).  Measured on B200:
+    // the TMEM kernel wins or ties whenever both use the same column-tile width (all GEMMs at
+    // H = 384: 18.4 vs 19.6 ms per layer), the shared-memory kernel wins where it can use
+    // 256-wide tiles (H = 768: TMEM holds at most 2 x 192 accumulator columns + the A ring).
+    // RUVGNN_TC_TS = 0 never / 1 always / unset: that rule.
+    static int ts = -2;
+    if (ts == -2) {
       const char *e = getenv("RUVGNN_TC_TS");
-      ts = (e && atoi(e) == 1) ? 1 : 0;
+      ts = e ? atoi(e) : -1;
     }
-    if (ts && maps->ts_ok[which]) {
+    const bool use_ts = ts == 1 || (ts == -1 && maps->block_n3[which] == maps->block_n[which]);
+    if (use_ts && maps->ts_ok[which]) {
       if (launches) ++*launches;
       return launch_gemm_tc_ts(g, epi, *maps, which, single_pass, sm_count, s);
     }

@@ -5,7 +5,7 @@
 // producer warps store the split A tile -- more than the 128 B/cycle an SM's shared memory
 // moves.  Here the activation tile never touches shared memory:
 //   warps 2-5   A producers: each thread owns ONE row of the 128-row tile, loads its 32-float
-//               k-block (8 x LDG.128), splits hi/lo in registers and writes both with
+//               k-block (4 x 256-bit LDG), splits hi/lo in registers and writes both with
 //               tcgen05.st.32x32b.x32 into a ring of TMEM column blocks
 //   warp 1      MMA issuer: tcgen05.mma ... [d_tmem], [a_tmem], b_desc  (A from TMEM, B from smem)
 //   warp 0      TMA producer for W_hi / W_lo (shared memory now holds only weight stages)
@@ -193,10 +193,20 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap map_hi,
         src = g.A1 + row * g.lda1 + k0;
       else
         src = g.A2 + row * g.lda2 + (k0 - g.K1);
+      if (row < g.M) {
+        // 256-bit loads: a thread reads its row's 128 contiguous bytes in 4 instructions, so the
+        // warp's 32 rows cost 4 x 32 L1 wavefronts per k-block instead of 8 x 32.
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = row < g.M ? __ldg(reinterpret_cast<const float4 *>(src) + i)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i)
+          asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=f"(v[2 * i].x), "=f"(v[2 * i].y), "=f"(v[2 * i].z), "=f"(v[2 * i].w),
+                         "=f"(v[2 * i + 1].x), "=f"(v[2 * i + 1].y), "=f"(v[2 * i + 1].z),
+                         "=f"(v[2 * i + 1].w)
+                       : "l"(src + 8 * i));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
     int tile = blockIdx.x, kb = 0;
     if (tile < num_tiles) issue(nxt, tile, 0);
