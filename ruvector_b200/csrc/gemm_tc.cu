@@ -469,6 +469,19 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       maps->ts_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
     }
+    maps->pair_ts_ok[i] = false;
+    if (maps->block_n3[i] > 0 && maps->block_n3[i] % 32 == 0) {
+      const cuuint32_t box4[2] = {32u, (cuuint32_t)(maps->block_n3[i] / 2)};
+      CUresult r1 = encode(&maps->hi4[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->hi[i], dims,
+                           strides, box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r2 = encode(&maps->lo4[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->lo[i], dims,
+                           strides, box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      maps->pair_ts_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+    }
   }
   out->tmaps = maps;
   out->usable = true;
@@ -501,6 +514,10 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
     if (ts == -2) {
       const char *e = getenv("RUVGNN_TC_TS");
       ts = e ? atoi(e) : -1;
+    }
+    if (ts == 2 && maps->pair_ts_ok[which] && sm_count >= 2) {  // RUVGNN_TC_TS=2: pair + TMEM-A
+      if (launches) ++*launches;
+      return launch_gemm_tc_pair_ts(g, epi, *maps, which, single_pass, sm_count, s);
     }
     const bool use_ts = ts == 1 || (ts == -1 && maps->block_n3[which] == maps->block_n[which]);
     if (use_ts && maps->ts_ok[which]) {

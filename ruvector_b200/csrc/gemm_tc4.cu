@@ -1,0 +1,386 @@
+// CTA-pair (cta_group::2) + A-in-TMEM variant of the tcgen05 3xTF32 GEMM.
+//
+// Combines gemm_tc2.cu (two CTAs own 256 consecutive rows of one column tile, each streams only
+// HALF of the weight k-block, one tcgen05.mma.cta_group::2 with M = 256 issued by the leader)
+// with gemm_tc3.cu (the split activation tile goes registers -> TMEM with tcgen05.st, shared
+// memory carries weights only).  Per SM and k-block this ingests 16 KB of A + BN/2 x 256 B of
+// weights -- the smallest operand stream of the four kernels.
+//   full_a[s]   leader's, 8 arrivals (4 A-producer warps per CTA, remote arrive)
+//   full_b[s]   leader's, 1 arrival (expect_tx) + TMA bytes from both CTAs
+//   empty_a/b   each CTA's own, signalled by tcgen05.commit ... multicast::cluster
+//   tmem_full   each CTA's own (multicast commit); tmem_empty: leader's, 8 epilogue warps
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace ruvgnn {
+namespace tc {
+namespace {
+
+constexpr int BK = 32;
+
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: address in the even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) &
+                                                                                  kPeerMask)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+// tcgen05.commit to the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T over the CTA pair (M = 256)
+__device__ __forceinline__ void umma_tf32_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32_pair(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | (16u << 24);
+}
+
+struct Tc4Params {
+  TcParams p;
+  int a_stages, b_stages;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_pair_ts_kernel(const __grid_constant__ CUtensorMap map_hi,
+                       const __grid_constant__ CUtensorMap map_lo, const Tc4Params q) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const TcParams &p = q.p;
+  const GemmArgs &g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int BN = p.block_n, HN = BN / 2, SA = q.a_stages, SB = q.b_stages;
+  const int b_tile_bytes = HN * BK * 4;  // this CTA's half of one weight k-block copy
+  const size_t stage_bytes = 2 * (size_t)b_tile_bytes;
+
+  uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~(uintptr_t)1023);
+  auto b_hi = [&](int s) { return base + s * stage_bytes; };
+  auto b_lo = [&](int s) { return base + s * stage_bytes + b_tile_bytes; };
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)SB * stage_bytes);
+  uint64_t *full_b = bars, *empty_b = bars + MAX_STAGES;
+  uint64_t *full_a = bars + 2 * MAX_STAGES, *empty_a = bars + 3 * MAX_STAGES;
+  uint64_t *tmem_full = bars + 4 * MAX_STAGES, *tmem_empty = bars + 4 * MAX_STAGES + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 4 * MAX_STAGES + 4);
+  float *stile = reinterpret_cast<float *>(bars + 4 * MAX_STAGES + 6) +
+                 (warp >= 6 ? warp - 6 : 0) * EPI_TILE_FLOATS;
+
+  const uint32_t need_cols = 2 * BN + 64 * SA;
+  const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
+                             : need_cols <= 256 ? 256 : 512;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_lo)) : "memory");
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
+    }
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&full_a[s], 8);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_pair(tmem_ptr, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t a_col0 = (uint32_t)(2 * BN);
+
+  const int K = g.K1 + g.K2;
+  const int num_kb = K / BK;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // m tiles are 256 rows
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's half of the weight k-block =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * HN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_b[stage], phase ^ 1);
+          if (leader)
+            mbar_arrive_expect_tx(&full_b[stage], (p.single_pass ? 1u : 2u) * 2u * (uint32_t)b_tile_bytes);
+          tma_load_2d_pair(b_hi(stage), &map_hi, &full_b[stage], kb * BK, n0);
+          if (!p.single_pass) tma_load_2d_pair(b_lo(stage), &map_lo, &full_b[stage], kb * BK, n0);
+          if (++stage == SB) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only; A from TMEM (both CTAs), B halves from both smems =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_pair(BN);
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_a[sa], pa);
+          mbar_wait(&full_b[sb], pb);
+          tc_fence_after();
+          const uint32_t ah = tmem_base + a_col0 + (uint32_t)(sa * 64);
+          const uint32_t al = ah + 32;
+          const uint64_t bh = make_desc<BK>(smem_u32(b_hi(sb)));
+          const uint64_t bl = make_desc<BK>(smem_u32(b_lo(sb)));
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t off = (uint64_t)((kk * 32) >> 4);
+            const uint32_t first = (kb | kk) ? 1u : 0u;
+            if (p.single_pass) {
+              umma_tf32_pair_ts(d, ah + kk * 8, bh + off, idesc, first);
+            } else {
+              umma_tf32_pair_ts(d, al + kk * 8, bh + off, idesc, first);
+              umma_tf32_pair_ts(d, ah + kk * 8, bl + off, idesc, 1u);
+              umma_tf32_pair_ts(d, ah + kk * 8, bh + off, idesc, 1u);
+            }
+          }
+          umma_commit_pair(&empty_a[sa]);
+          umma_commit_pair(&empty_b[sb]);
+          if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc]);
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1;
+          }
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== A producers: one row per thread of this CTA's 128 rows -> (hi, lo) -> own TMEM =====
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    float4 cur[8], nxt[8];
+    auto issue = [&](float4 (&v)[8], int tile, int kb) {
+      const int64_t row = (int64_t)(tile / p.num_n_tiles) * (2 * BLOCK_M) + (int64_t)rank * BLOCK_M + row_in_tile;
+      const int k0 = kb * BK;
+      const float *src;
+      if (k0 < g.K1)
+        src = g.A1 + row * g.lda1 + k0;
+      else
+        src = g.A2 + row * g.lda2 + (k0 - g.K1);
+      if (row < g.M) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=f"(v[2 * i].x), "=f"(v[2 * i].y), "=f"(v[2 * i].z), "=f"(v[2 * i].w),
+                         "=f"(v[2 * i + 1].x), "=f"(v[2 * i + 1].y), "=f"(v[2 * i + 1].z),
+                         "=f"(v[2 * i + 1].w)
+                       : "l"(src + 8 * i));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int tile = pair, kb = 0;
+    if (tile < num_tiles) issue(nxt, tile, 0);
+    while (tile < num_tiles) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      int ntile = tile, nkb = kb + 1;
+      if (nkb == num_kb) {
+        nkb = 0;
+        ntile = tile + num_pairs;
+      }
+      if (ntile < num_tiles) issue(nxt, ntile, nkb);
+      mbar_wait(&empty_a[stage], phase ^ 1);
+      tc_fence_after();
+      const uint32_t ah = tmem_base + lane_base + a_col0 + (uint32_t)(stage * 64);
+      uint32_t r[32];
+      const float *cf = reinterpret_cast<const float *>(cur);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = (__float_as_uint(cf[i]) + 0x1000u) & 0xFFFFE000u;
+      tmem_st32(ah, r);
+      if (!p.single_pass) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(cf[i] - __uint_as_float(r[i]));
+        tmem_st32(ah + 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&full_a[stage]);
+      if (++stage == SA) {
+        stage = 0;
+        phase ^= 1;
+      }
+      tile = ntile;
+      kb = nkb;
+    }
+  } else {
+    // ===== epilogue: this CTA's 128 accumulator rows =====
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int64_t row = (int64_t)(tile / p.num_n_tiles) * (2 * BLOCK_M) + (int64_t)rank * BLOCK_M + row_in_tile;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const int64_t row0 = row - lane;
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        if (row0 >= g.M) continue;
+        epilogue_chunk<EPI>(g, row0, n0 + c, v, stile, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+template <int EPI>
+cudaError_t launch_pair_ts_epi(const CUtensorMap &hi, const CUtensorMap &lo, const Tc4Params &q, int grid,
+                               size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_ts_kernel<EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gemm_tc_pair_ts_kernel<EPI><<<grid, NUM_THREADS, smem, s>>>(hi, lo, q);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gemm_tc_pair_ts(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
+                                   bool single_pass, int sm_count, cudaStream_t s) {
+  Tc4Params q;
+  TcParams &p = q.p;
+  p.g = g;
+  p.block_n = maps.block_n3[which];
+  p.single_pass = single_pass ? 1 : 0;
+  p.debug = 0;
+  p.stages = 0;
+  p.num_m_tiles = (int)((g.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+  p.num_n_tiles = g.N / p.block_n;
+  q.a_stages = (512 - 2 * p.block_n) / 64;
+  if (q.a_stages > 4) q.a_stages = 4;
+  if (q.a_stages < 2) return cudaErrorInvalidValue;
+  const size_t stage_bytes = 2 * (size_t)(p.block_n / 2) * BK * 4;
+  const size_t fixed = 1024 + 384 + 4 * EPI_TILE_FLOATS * sizeof(float);
+  int sb = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (sb > MAX_STAGES) sb = MAX_STAGES;
+  if (sb < 2) return cudaErrorInvalidValue;
+  q.b_stages = sb;
+  const size_t smem = sb * stage_bytes + fixed;
+  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
+  int pairs = sm_count / 2;
+  if (tiles < pairs) pairs = (int)tiles;
+  const int grid = 2 * pairs;
+  switch (epi) {
+    case EPI_BIAS:
+      return launch_pair_ts_epi<EPI_BIAS>(maps.hi4[which], maps.lo4[which], q, grid, smem, s);
+    case EPI_BIAS_ADD:
+      return launch_pair_ts_epi<EPI_BIAS_ADD>(maps.hi4[which], maps.lo4[which], q, grid, smem, s);
+    case EPI_GATES:
+      return launch_pair_ts_epi<EPI_GATES>(maps.hi4[which], maps.lo4[which], q, grid, smem, s);
+    case EPI_GRU:
+      return launch_pair_ts_epi<EPI_GRU>(maps.hi4[which], maps.lo4[which], q, grid, smem, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace tc
+}  // namespace ruvgnn

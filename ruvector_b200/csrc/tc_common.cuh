@@ -305,11 +305,13 @@ struct TcMaps {
   CUtensorMap hi[TC_W_COUNT], lo[TC_W_COUNT];    // box {block_k, block_n}
   CUtensorMap hi2[TC_W_COUNT], lo2[TC_W_COUNT];  // box {32, block_n/2}: CTA-pair kernel
   CUtensorMap hi3[TC_W_COUNT], lo3[TC_W_COUNT];  // box {32, block_n3}: A-in-TMEM kernel
+  CUtensorMap hi4[TC_W_COUNT], lo4[TC_W_COUNT];  // box {32, block_n3/2}: pair + A-in-TMEM kernel
   int block_n[TC_W_COUNT];
   int block_n3[TC_W_COUNT];
   int block_k;
   bool pair_ok[TC_W_COUNT];
   bool ts_ok[TC_W_COUNT];
+  bool pair_ts_ok[TC_W_COUNT];
 };
 
 // Which epilogue kinds use the coalesced (smem-transposed) form: bit e = EpiKind e.
@@ -320,6 +322,10 @@ int tc_epi_mask();
 int pick_block_n_ts(uint32_t n);
 cudaError_t launch_gemm_tc_ts(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
                               bool single_pass, int sm_count, cudaStream_t s);
+
+// CTA-pair + A-in-TMEM launcher, gemm_tc4.cu
+cudaError_t launch_gemm_tc_pair_ts(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
+                                   bool single_pass, int sm_count, cudaStream_t s);
 
 // CTA-pair (cta_group::2) launcher, gemm_tc2.cu
 cudaError_t launch_gemm_tc_pair(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
