@@ -343,7 +343,8 @@ def main():
     roof = {"kernel": f"{'gather_r1_kernel' if R == 1 else 'gather_fast_kernel'} (K-agg, R={R})", "bound": "hbm",
             "achieved": (bytes_launch / (agg_ms * 1e-3) / 1e9) if agg_ms else None, "peak": peak, "unit": "GB/s",
             "frac": (bytes_launch / (agg_ms * 1e-3) / 1e9 / peak) if agg_ms else None,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
+            "traffic": None, "peak_source": peak_src,
+            "frac_of_nominal_8TBs": (bytes_launch / (agg_ms * 1e-3) / 1e9 / 8000.0) if agg_ms else None, "algorithmic_bytes_per_launch": bytes_launch,
             "kernel_ms": agg_ms, "stage_ms": {"project": float(stage[0]), "aggregate": float(stage[1]),
                                                "update": float(stage[2])}}
     traffic_file = ROOT / "profiles" / "kagg_traffic.json"
@@ -372,6 +373,10 @@ def main():
     if not a.no_cpu_baseline and world == 1:
         cb, _, _ = cpu_baseline(a, layer, x, g, a.cpu_seconds)
         line["cpu_baseline"] = cb
+        # the reference itself is single-threaded (no rayon / SIMD use in crates/ruvector-gnn/src):
+        # the same faithful loop on ONE host thread, short sample
+        c1, _, _ = cpu_baseline(a, layer, x, g, 4.0, threads=1)
+        line["cpu_baseline_single_thread"] = c1
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
