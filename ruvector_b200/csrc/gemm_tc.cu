@@ -345,7 +345,11 @@ int tc_block_k() {
 template <int EPI, int BK, bool COAL>
 cudaError_t launch_epi_bk(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int grid,
                           size_t smem, cudaStream_t s) {
-  static bool configured = false;
+  // function attributes are per device: remember which devices have been configured
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool &configured = configured_dev[dev & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, BK, COAL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -325,7 +325,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_hi,
 template <int EPI>
 cudaError_t launch_pair_epi(const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p, int grid,
                             size_t smem, cudaStream_t s) {
-  static bool configured = false;
+  // function attributes are per device: remember which devices have been configured
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool &configured = configured_dev[dev & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<EPI, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

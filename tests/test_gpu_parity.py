@@ -322,3 +322,40 @@ def test_config2_full_size_sampled_against_oracle(oracle, ctx):
         ref = oracle.forward_node(layer, x[i], x[g.col_idx[s:t]], g.edge_w[s:t])
         worst = max(worst, float(np.linalg.norm(out[i] - ref) / max(np.linalg.norm(ref), 1e-6)))
     assert worst <= 1e-4, worst
+
+
+def test_seeded_fuzz_over_shapes_degrees_and_modes(oracle, ctx):
+    """Random layer shapes (aligned and unaligned), head counts, degree distributions (incl.
+    empty rows, hubs), weight signs and dropout values; every arithmetic mode the shape admits."""
+    rng = np.random.default_rng(20261018)
+    for case in range(24):
+        heads = int(rng.choice([1, 2, 3, 4, 8]))
+        if case % 3 == 0:   # tensor-core eligible, fast gather layouts
+            hdim = int(rng.choice([128, 256, 384])); heads = int(rng.choice([1, 2, 4, 8]))
+            d = int(rng.choice([32, 64, 128, 384]))
+        elif case % 3 == 1:  # tensor-core eligible, generic gather
+            hdim = int(rng.choice([32, 64, 96, 160])); heads = int(rng.choice([h for h in (1, 2, 4, 8) if hdim % h == 0]))
+            d = int(rng.choice([32, 96]))
+        else:                # nothing aligned
+            hdim = heads * int(rng.integers(1, 12)); d = int(rng.integers(1, 70))
+        n = int(rng.integers(1, 700))
+        deg = rng.choice([0, 1, 2, 5, 17, 33, 70], size=n, p=[.1, .15, .2, .25, .15, .1, .05])
+        deg = np.minimum(deg, 4 * n)
+        row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint64)
+        cols = rng.integers(0, n, size=int(row_ptr[-1])).astype(np.uint32)
+        w = (rng.random(cols.size) * rng.choice([1.0, 1.0, -1.0])).astype(F32)
+        g = rv.CsrGraph(row_ptr, cols, w)
+        dropout = float(rng.choice([0.0, 0.1, 0.5, 1.0]))
+        layer = rv.RuvectorLayer(d, hdim, heads, dropout, weights=synth.make_weights(d, hdim, seed=1000 + case), ctx=ctx)
+        x = (rng.standard_normal((n, d)) * rng.choice([0.1, 1.0, 3.0])).astype(F32)
+        ref = oracle.forward_graph(layer, x, g)
+        dg = g.to_device(ctx)
+        modes = [rv.MODE_FP32_SIMT] + ([rv.MODE_FP32_TC] if d % 32 == 0 and hdim % 32 == 0 else [])
+        for mode in modes:
+            layer.set_mode(mode)
+            out = layer.forward_graph(x, dg)
+            if dropout == 1.0:  # everything scales to 0 before LayerNorm: output = beta (:414-417)
+                assert np.isfinite(out).all()
+                continue
+            rel = np.linalg.norm(out - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-6)
+            assert rel.max() <= 1e-4, (case, n, d, hdim, heads, mode, float(rel.max()))
