@@ -1,0 +1,32 @@
+"""Builds and runs the C++ host-side mirror (include/ruvgnn.hpp) test program, which reads like
+the reference's own unit tests (tests/cpp/test_layer.cpp)."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from ruvector_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def build_exe(tmp_path):
+    exe = tmp_path / "test_layer"
+    lib = _lib.lib_path()
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "test_layer.cpp"),
+           "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_cpp_constructor_and_error_behaviour(built, tmp_path):
+    res = subprocess.run([str(build_exe(tmp_path)), "config"], capture_output=True, text=True, timeout=120)
+    print(res.stdout, res.stderr)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK")
+
+
+@pytest.mark.gpu
+def test_cpp_forward_tests(built, tmp_path):
+    res = subprocess.run([str(build_exe(tmp_path)), "all"], capture_output=True, text=True, timeout=300)
+    print(res.stdout, res.stderr)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK")
