@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--heads", type=int, default=8)
     ap.add_argument("--m", type=int, default=32)
     ap.add_argument("--locality", type=float, default=0.0)
+    ap.add_argument("--window", type=int, default=4096, help="id window of the local neighbours (with --locality)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: do not run interior rows under the halo exchange")
     ap.add_argument("--mode", type=int, default=-1, help="-1: best parity mode available")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -147,7 +149,7 @@ def build_inputs(a, rank, world):
 
     x = synth.make_features(a.nodes, a.dim, seed=0x5EED + rank)
     # rank r owns rows [r*nodes, (r+1)*nodes) of a (world*nodes)-node graph; columns are global
-    g = synth.hnsw_like_graph(a.nodes, a.m, seed=0xBEEF + rank, locality=a.locality,
+    g = synth.hnsw_like_graph(a.nodes, a.m, seed=0xBEEF + rank, locality=a.locality, window=a.window,
                               n_total=a.nodes * world, row_offset=rank * a.nodes)
     w = synth.make_weights(a.dim, a.dim)
     return x, g, w
@@ -239,7 +241,7 @@ def main():
     if world > 1:
         from ruvector_b200 import dist as rvdist
 
-        part = rvdist.Partition.build(g, rank, world, a.nodes, ctx)
+        part = rvdist.Partition.build(g, rank, world, a.nodes, ctx, overlap=not a.no_overlap)
 
         def step_fn(xd, od, timing=False):
             ctx.set_timing(timing)
@@ -361,7 +363,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, n_gpus), "nodes_per_gpu": n, "dim": H, "heads": a.heads, "m": a.m,
-                   "edges": E_total, "locality": a.locality, "l2": "inputs larger than L2 (X, projected rows >> 126 MB)",
+                   "edges": E_total, "locality": a.locality, "window": a.window, "l2": "inputs larger than L2 (X, projected rows >> 126 MB)",
                    "projection_mode": {0: "fp32_simt", 1: "fp32_3xtf32_tcgen05", 2: "tf32_tcgen05"}[mode],
                    "parallelism": f"range-partition x{n_gpus}" if n_gpus > 1 else "single"},
         "edges_per_sec": E_total / (ms_per_step * 1e-3),
@@ -369,7 +371,10 @@ def main():
     }
     if world > 1:
         line["halo"] = {"rows_received_rank0": part.plan.n_halo, "rows_sent_rank0": int(part.plan.send_idx.size),
-                        "bytes_exchanged_rank0": int(part.bytes_exchanged), "exchange_ms_rank0": exchange_ms}
+                        "bytes_exchanged_rank0": int(part.bytes_exchanged), "exchange_ms_rank0": exchange_ms,
+                        "plane": "all-gather" if part.dense else "all-to-all-v",
+                        "interior_rows_rank0": int(part.interior_rows), "overlap": not a.no_overlap,
+                        "exposed_wait_ms_rank0": round(part.exposed_wait_ms(), 3)}
     if not a.no_cpu_baseline and world == 1:
         cb, _, _ = cpu_baseline(a, layer, x, g, a.cpu_seconds)
         line["cpu_baseline"] = cb

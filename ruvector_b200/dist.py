@@ -143,6 +143,37 @@ def choose_dense(plan: HaloPlan, threshold: float = 0.75, group=None) -> bool:
     return bool(t.item() >= threshold)
 
 
+def interior_runs(plan: HaloPlan, min_rows: int = 1024, max_runs: int = 4):
+    """Split the local rows into *interior* ranges (every neighbour of every row is a local
+    row, so they can be aggregated while the halo is still in flight) and *boundary* ranges.
+
+    Range partitions of a locality-ordered graph have their boundary rows at the two ends of
+    the range, so interior rows are taken as the (at most ``max_runs``) longest contiguous runs
+    of >= ``min_rows`` interior rows: contiguous ranges keep every kernel of the path on
+    plain row blocks (no row permutation, no indirection).  Returns ``(interior, boundary)``,
+    two sorted lists of ``(begin, end)`` that together tile ``[0, n_local)``."""
+    n = plan.n_local
+    if n == 0:
+        return [], []
+    remote = (plan.graph.col_idx >= n).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(remote)])
+    rp = plan.graph.row_ptr.astype(np.int64)
+    is_int = (cs[rp[1:]] - cs[rp[:-1]]) == 0
+    edge = np.flatnonzero(np.diff(np.concatenate([[0], is_int.view(np.int8), [0]])))
+    starts, ends = edge[0::2], edge[1::2]
+    keep = np.flatnonzero(ends - starts >= max(min_rows, 1))
+    keep = keep[np.argsort(-(ends - starts)[keep], kind="stable")[:max_runs]]
+    interior = sorted((int(starts[k]), int(ends[k])) for k in keep)
+    boundary, at = [], 0
+    for a, b in interior:
+        if a > at:
+            boundary.append((at, a))
+        at = b
+    if at < n:
+        boundary.append((at, n))
+    return interior, boundary
+
+
 def dense_columns(plan: HaloPlan) -> np.ndarray:
     """Column indices for the all-gather data plane: own rows stay local, remote row with
     global id g is addressed as ``n_local + g`` (the gathered block is in global order)."""
@@ -159,9 +190,14 @@ class Partition:
     Two data planes with identical results: ``sparse`` = pack the rows each peer asked for
     and exchange them with one all-to-all-v; ``dense`` = copy the whole projected K|V|M
     block contiguously and all-gather it (chosen collectively when the halo is almost
-    everything, see :func:`choose_dense`)."""
+    everything, see :func:`choose_dense`).
 
-    def __init__(self, plan: HaloPlan, ctx, dense: bool = False):
+    ``overlap``: the collective is issued asynchronously (NCCL runs it on its own stream) and
+    the interior row ranges (:func:`interior_runs`) are aggregated and updated while it is in
+    flight; the launching stream then waits for the halo and finishes the boundary ranges.
+    Each row sees exactly the same arithmetic either way."""
+
+    def __init__(self, plan: HaloPlan, ctx, dense: bool = False, overlap: bool = True):
         import torch
 
         from .graph import CsrGraph
@@ -177,11 +213,22 @@ class Partition:
             self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
         self._send = self._halo = self._x = self._out = None
         self.bytes_exchanged = 0
+        self.interior, self.boundary = interior_runs(plan) if overlap else ([], [(0, plan.n_local)] if plan.n_local else [])
+        self.interior_rows = sum(b - a for a, b in self.interior)
+        self._wait_ev = None
 
     @classmethod
-    def build(cls, local_rows: CsrGraph, rank: int, world: int, n_per_rank: int, ctx) -> "Partition":
+    def build(cls, local_rows: CsrGraph, rank: int, world: int, n_per_rank: int, ctx, overlap: bool = True) -> "Partition":
         plan = exchange_requests(HaloPlan.build(local_rows, rank, even_bounds(n_per_rank * world, world)))
-        return cls(plan, ctx, dense=choose_dense(plan))
+        return cls(plan, ctx, dense=choose_dense(plan), overlap=overlap)
+
+    def exposed_wait_ms(self) -> float:
+        """Device time the launching stream spent waiting for the halo in the last forward
+        (the part of the exchange that interior compute did not hide).  Synchronises."""
+        if self._wait_ev is None:
+            return 0.0
+        self._wait_ev[1].synchronize()
+        return float(self._wait_ev[0].elapsed_time(self._wait_ev[1]))
 
     def forward(self, layer, x_dev, out_dev, timing: bool = False):
         """project -> pack -> all-to-all-v (NCCL) -> gather/aggregate + update.  Enqueue only."""
@@ -201,20 +248,38 @@ class Partition:
         if n_send:
             _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
                                             C.c_void_p(self._send.data_ptr())))
-        if self.dense:
-            import torch.distributed as dist
+        import torch.distributed as dist
 
+        work = None
+        if self.dense:
             n_total = int(plan.bounds[-1])
             if self._halo is None or self._halo.shape != (n_total, W):
                 self._halo = torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
-            dist.all_gather_into_tensor(self._halo, self._send)
+            work = dist.all_gather_into_tensor(self._halo, self._send, async_op=True)
             self.bytes_exchanged = (n_total - plan.n_local) * W * 4 * 2
         else:
-            self._halo = exchange_rows(plan, self._send)
+            if self._halo is None or self._halo.shape != (plan.n_halo, W):
+                self._halo = torch.empty((plan.n_halo, W), dtype=torch.float32, device=x_dev.device)
+            if plan.world > 1:
+                work = dist.all_to_all_single(self._halo, self._send, plan.recv_counts.tolist(),
+                                              plan.send_counts.tolist(), async_op=True)
             self.bytes_exchanged = (n_send + plan.n_halo) * W * 4
         halo_ptr = self._halo.data_ptr() if (plan.n_halo or self.dense) else None
-        _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr), 0,
-                                                     plan.n_local, C.c_void_p(out_dev.data_ptr())))
+
+        def rows(a, b):
+            _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr),
+                                                         a, b, C.c_void_p(out_dev.data_ptr())))
+
+        for a, b in self.interior:  # no remote neighbour: runs while the collective is in flight
+            rows(a, b)
+        if self._wait_ev is None:
+            self._wait_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._wait_ev[0].record()
+        if work is not None:
+            work.wait()  # the launching stream waits for the halo; the host does not block
+        self._wait_ev[1].record()
+        for a, b in self.boundary:
+            rows(a, b)
 
     def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray):
         """Host buffers in, host buffers out (H2D / D2H inside): the e2e leg of bench.py."""

@@ -27,7 +27,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
     for (n, d, heads, m, mode, loc) in [(6000, 128, 4, 16, rv.MODE_FP32_SIMT, 0.0), (5000, 384, 8, 16, rv.MODE_FP32_TC, 0.5),
-                                        (4001, 128, 4, 8, rv.MODE_FP32_TC, 0.9)]:
+                                        (4001, 128, 4, 8, rv.MODE_FP32_TC, 0.9),
+                                        # pure id-window graph: most rows are interior and run under the exchange
+                                        (12000, 384, 8, 16, rv.MODE_FP32_TC, 1.0)]:
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         ctx = rv.Context(local, stream.cuda_stream)
@@ -45,6 +47,11 @@ def main():
         od = torch.empty(hi - lo, d, device="cuda")
         part.forward(layer, xd, od)
         torch.cuda.synchronize()
+        # same rows without the interior/boundary split (exchange not overlapped): identical bits
+        od2 = torch.empty_like(od)
+        rvdist.Partition(plan, ctx, dense=dense, overlap=False).forward(layer, xd, od2)
+        torch.cuda.synchronize()
+        same_split = bool(torch.equal(od, od2)) and (loc < 1.0 or part.interior_rows > 0)
         sizes = [int(bounds[p + 1] - bounds[p]) for p in range(world)]
         full = torch.empty(n, d, device="cuda")
         dist.all_gather(list(full.split(sizes)), od)
@@ -61,11 +68,13 @@ def main():
             single = layer.forward_graph(x, g.to_device(ctx))
             bit = np.array_equal(single, got)
             print(f"n={n} d={d} mode={mode} locality={loc}: world={world} dense={dense} halo_rows={part.plan.n_halo} "
-                  f"max_row_rel={rel.max():.2e} bit_identical_to_single_gpu={bit} host_variant_same={same_host}")
+                  f"interior_rows={part.interior_rows} max_row_rel={rel.max():.2e} bit_identical_to_single_gpu={bit} "
+                  f"host_variant_same={same_host}")
             ok = ok and rel.max() <= 1e-4 and bit and same_host
+        ok = ok and same_split
         torch.cuda.set_stream(torch.cuda.default_stream())
     flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if rank == 0:
         print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")

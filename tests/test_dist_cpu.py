@@ -119,3 +119,33 @@ def test_partition_rows_generator_matches_global_semantics():
         row = part.col_idx[s:e]
         assert (400 + i) not in row and len(set(row.tolist())) == len(row)
     assert (part.col_idx >= 600).any() and (part.col_idx < 400).any()  # references other partitions
+
+
+def test_interior_runs_tile_the_local_rows_and_touch_no_halo():
+    n, world = 6000, 3
+    g = synth.hnsw_like_graph(n, 8, seed=5, locality=1.0, window=40, iso_frac=0.02)
+    bounds = rvdist.even_bounds(n, world)
+    for rank in range(world):
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        plan = rvdist.HaloPlan.build(_slice_rows(g, lo, hi), rank, bounds)
+        interior, boundary = rvdist.interior_runs(plan, min_rows=64, max_runs=3)
+        both = sorted(interior + boundary)
+        assert both[0][0] == 0 and both[-1][1] == plan.n_local
+        assert all(a[1] == b[0] for a, b in zip(both, both[1:])) and all(b > a for a, b in both)
+        rp = plan.graph.row_ptr.astype(np.int64)
+        for a, b in interior:
+            assert b - a >= 64
+            assert (plan.graph.col_idx[rp[a]:rp[b]] < plan.n_local).all()
+        # a +-40 id window leaves at most ~40 rows at each end of the range on the boundary
+        assert sum(b - a for a, b in interior) >= plan.n_local - 2 * 40 - 2
+        # every run is maximal: the row just outside an interior run has a remote neighbour
+        for a, b in interior:
+            if a > 0:
+                assert (plan.graph.col_idx[rp[a - 1]:rp[a]] >= plan.n_local).any()
+    # insertion-order worst case: nothing is interior; tiny min_rows keeps at most max_runs runs
+    g0 = synth.hnsw_like_graph(n, 8, seed=6, locality=0.0)
+    plan0 = rvdist.HaloPlan.build(_slice_rows(g0, 0, int(bounds[1])), 0, bounds)
+    interior0, boundary0 = rvdist.interior_runs(plan0, min_rows=64)
+    assert interior0 == [] and boundary0 == [(0, plan0.n_local)]
+    few, rest = rvdist.interior_runs(plan0, min_rows=1, max_runs=2)
+    assert len(few) <= 2 and sum(b - a for a, b in few + rest) == plan0.n_local
