@@ -214,6 +214,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # the collective shares the GPU with the kernels that run under it: cap its blocks at the SMs
+        # the partitioned forward leaves free (ruvector_b200.dist.Partition.comm_sms)
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("RUVGNN_COMM_SMS", "16"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 
@@ -289,6 +292,18 @@ def main():
         exchange_ms = t["exchange_ms"]
     except rv.GnnError:
         pass
+    if world > 1 and part.interior_rows > 0:
+        # the overlapped step runs K-agg once per row range, so its stage events cover the last
+        # range only: take the per-kernel times from one extra un-split pass over the same rows
+        whole = rvdist.Partition(part.plan, ctx, dense=part.dense, overlap=False)
+        for _ in range(2):
+            ctx.set_timing(True)
+            whole.forward(layer, x_dev, out_dev)
+        barrier()
+        t = ctx.last_timing()
+        stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
+        exchange_ms = whole.exposed_wait_ms()
+        del whole
     ctx.set_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:

@@ -62,6 +62,10 @@ uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *ctx);
  * 5 halo exchange wait), averaged over the timed forwards (up to 32) since the
  * previous query; CUDA events on the launching stream.  Synchronises the stream. */
 int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *ctx, float *ms6);
+/* Launch grids sized for at most `sms` SMs (0 = all of the device; negative = all but
+ * |sms|): leaves SMs to a collective that runs concurrently on another stream, so persistent
+ * kernels do not queue behind its blocks. */
+int32_t ruvgnn_ctx_set_sm_limit(ruvgnn_ctx *ctx, int32_t sms);
 /* Also time the phased entries (ruvgnn_layer_project / ruvgnn_layer_aggregate_update). */
 int32_t ruvgnn_ctx_set_timing(ruvgnn_ctx *ctx, int32_t on);
 
@@ -235,6 +239,19 @@ uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *layer);
  * [n_idx][ruvgnn_layer_halo_width] device buffer (the halo send buffer). */
 int32_t ruvgnn_halo_pack(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, const uint32_t *idx_dev,
                          uint64_t n_idx, float *send_dev);
+/* Message-only halo (used when almost every remote row is needed): instead of moving K|V|M
+ * rows (3*hidden_dim floats) peers exchange the message rows M = W_msg x + b (hidden_dim
+ * floats) and rebuild K and V where they arrive.
+ * ruvgnn_layer_messages copies message rows [row_begin, row_begin + n_rows) of the projected
+ * block into a dense [n_rows][hidden_dim] device buffer.
+ * ruvgnn_layer_expand_halo turns received message rows into halo rows
+ * [W_k m + b_k | W_v m + b_v | m] ([n_rows][ruvgnn_layer_halo_width]; a plain copy for
+ * layers whose halo width is hidden_dim) with the very GEMM arithmetic of
+ * ruvgnn_layer_project (layer.rs:136-137), so the rebuilt rows carry the owner's bits. */
+int32_t ruvgnn_layer_messages(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, uint64_t row_begin,
+                              uint64_t n_rows, float *out_dev);
+int32_t ruvgnn_layer_expand_halo(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
+                                 const float *m_rows_dev, uint64_t n_rows, float *halo_dev);
 /* Phase B: gather/aggregate + update for local rows [row_begin,row_end).
  * graph col_idx < n_local address own rows, col_idx >= n_local address
  * halo_dev[col - n_local] ([n_halo][ruvgnn_layer_halo_width], received from peers). */

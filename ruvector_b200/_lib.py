@@ -40,6 +40,7 @@ SYMBOLS = {
     "ruvgnn_ctx_launch_count": (C.c_uint64, [_vp]),
     "ruvgnn_ctx_last_timing": (C.c_int32, [_vp, c_float_p]),
     "ruvgnn_ctx_set_timing": (C.c_int32, [_vp, C.c_int32]),
+    "ruvgnn_ctx_set_sm_limit": (C.c_int32, [_vp, C.c_int32]),
     "ruvgnn_layer_create": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(Weights), C.POINTER(_vp)]),
     "ruvgnn_layer_validate": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]),
     "ruvgnn_layer_from_json": (C.c_int32, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
@@ -66,6 +67,8 @@ SYMBOLS = {
     "ruvgnn_layer_project": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_halo_width": (C.c_uint32, [_vp]),
     "ruvgnn_halo_pack": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "ruvgnn_layer_messages": (C.c_int32, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),
+    "ruvgnn_layer_expand_halo": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_aggregate_update": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
 }
 

@@ -30,7 +30,8 @@ struct ruvgnn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  int sm_count = 148;
+  int sm_count = 148;      // SMs grids are sized for (ruvgnn_ctx_set_sm_limit)
+  int sm_count_dev = 148;  // SMs of the device
   uint64_t launches = 0;
   // activation workspace: P[n][4H] | OA[n][2H] | T0..T3[n][H]
   float *ws = nullptr;
@@ -512,9 +513,10 @@ int32_t upload_layer(ruvgnn_layer *L) {
     L->Wov = dev(Wov); L->bov = dev(bov);
   }
   // tcgen05 path: split copies (hi/lo) of the six device weight matrices
-  const float *mats[TC_W_COUNT] = {Wmsg, L->r1 ? Wqk : Wqkv, L->r1 ? Wov : Wo, Wagg, Wzr, Wh};
-  const uint32_t rows[TC_W_COUNT] = {H, L->r1 ? L->heads * H : 3 * H, H, H, 2 * H, H};
-  const uint32_t cols[TC_W_COUNT] = {D, H, L->r1 ? L->heads * H : H, H, 2 * H, 2 * H};
+  const float *mats[TC_W_COUNT] = {Wmsg, L->r1 ? Wqk : Wqkv, L->r1 ? Wov : Wo, Wagg, Wzr, Wh,
+                                   Wqkv + (size_t)H * H};
+  const uint32_t rows[TC_W_COUNT] = {H, L->r1 ? L->heads * H : 3 * H, H, H, 2 * H, H, 2 * H};
+  const uint32_t cols[TC_W_COUNT] = {D, H, L->r1 ? L->heads * H : H, H, 2 * H, 2 * H, H};
   cudaError_t e = tc_weights_create(mats, rows, cols, &L->tc);
   if (e != cudaSuccess)
     return fail(RUVGNN_ERR_CUDA, std::string("tc_weights_create: ") + cudaGetErrorString(e));
@@ -568,7 +570,7 @@ int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
                                      std::to_string(prop.major) + std::to_string(prop.minor));
   std::unique_ptr<ruvgnn_ctx> c(new ruvgnn_ctx());
   c->device = device;
-  c->sm_count = prop.multiProcessorCount;
+  c->sm_count = c->sm_count_dev = prop.multiProcessorCount;
   if (stream) {
     c->stream = static_cast<cudaStream_t>(stream);
   } else {
@@ -620,6 +622,13 @@ int32_t ruvgnn_sync(ruvgnn_ctx *c) {
 }
 void *ruvgnn_ctx_stream(ruvgnn_ctx *c) { return c ? c->stream : nullptr; }
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
+
+int32_t ruvgnn_ctx_set_sm_limit(ruvgnn_ctx *c, int32_t sms) {
+  if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
+  if (sms < 0) sms = c->sm_count_dev + sms > 1 ? c->sm_count_dev + sms : 1;  // reserve |sms|
+  c->sm_count = (sms == 0 || sms > c->sm_count_dev) ? c->sm_count_dev : sms;
+  return RUVGNN_OK;
+}
 
 int32_t ruvgnn_ctx_set_timing(ruvgnn_ctx *c, int32_t on) {
   if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
@@ -1080,6 +1089,56 @@ int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *i
   Ws w = carve(c, L, c->proj_rows);
   RUVGNN_CUDA_TRY(launch_pack_rows(w.halo_src, w.ldm, w.halo_w, idx_dev, n_idx, send_dev,
                                    c->stream, &c->launches));
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_messages(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t row_begin,
+                              uint64_t n_rows, float *out_dev) {
+  if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (n_rows == 0) return RUVGNN_OK;
+  if (!out_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (c->proj_rows == 0 || c->proj_H != L->H)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "ruvgnn_layer_project has not run for this layer");
+  if (row_begin + n_rows > c->proj_rows)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "row range out of bounds");
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  Ws w = carve(c, L, c->proj_rows);
+  const size_t rowb = (size_t)L->H * sizeof(float);
+  RUVGNN_CUDA_TRY(cudaMemcpy2DAsync(out_dev, rowb, w.m + row_begin * w.ldm,
+                                    (size_t)w.ldm * sizeof(float), rowb, n_rows,
+                                    cudaMemcpyDeviceToDevice, c->stream));
+  return RUVGNN_OK;
+}
+
+int32_t ruvgnn_layer_expand_halo(ruvgnn_ctx *c, const ruvgnn_layer *L, const float *m_rows,
+                                 uint64_t n_rows, float *halo_dev) {
+  if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (n_rows == 0) return RUVGNN_OK;
+  if (!m_rows || !halo_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  const uint32_t H = L->H;
+  const size_t rowb = (size_t)H * sizeof(float);
+  if (L->r1) {  // the halo row is the message row itself
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(halo_dev, m_rows, rowb * n_rows, cudaMemcpyDeviceToDevice,
+                                    c->stream));
+    return RUVGNN_OK;
+  }
+  GemmArgs g;  // K | V = M [W_k; W_v]^T + b: the K, V column blocks of the Q|K|V projection
+  g.M = (int64_t)n_rows;
+  g.N = (int32_t)(2 * H);
+  g.K1 = (int32_t)H;
+  g.A1 = m_rows;
+  g.lda1 = H;
+  g.W = L->Wqkv + (size_t)H * H;
+  g.bias = L->bqkv + H;
+  g.out = halo_dev;
+  g.ldo = 3 * (int64_t)H;
+  int32_t rc = run_gemm(c, L, g, EPI_BIAS, TC_W_KV);
+  if (rc) return rc;
+  RUVGNN_CUDA_TRY(cudaMemcpy2DAsync(halo_dev + 2 * H, 3 * rowb, m_rows, rowb, rowb, n_rows,
+                                    cudaMemcpyDeviceToDevice, c->stream));
   return RUVGNN_OK;
 }
 

@@ -5,7 +5,8 @@
 namespace ruvgnn {
 
 // The six device weight matrices of a layer, in the order upload_layer builds them.
-enum TcWeightId : int { TC_W_MSG = 0, TC_W_QKV, TC_W_O, TC_W_AGG, TC_W_ZR, TC_W_H, TC_W_COUNT };
+// TC_W_KV = rows [H, 3H) of the Q|K|V matrix: rebuilds K|V of received message rows (M-only halo)
+enum TcWeightId : int { TC_W_MSG = 0, TC_W_QKV, TC_W_O, TC_W_AGG, TC_W_ZR, TC_W_H, TC_W_KV, TC_W_COUNT };
 
 // Per matrix: W_hi (TF32-representable part) and W_lo = W - W_hi, both [rows][cols]
 // row-major on the device, plus the TMA descriptors that stream them.

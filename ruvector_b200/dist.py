@@ -174,13 +174,29 @@ def interior_runs(plan: HaloPlan, min_rows: int = 1024, max_runs: int = 4):
     return interior, boundary
 
 
-def dense_columns(plan: HaloPlan) -> np.ndarray:
-    """Column indices for the all-gather data plane: own rows stay local, remote row with
-    global id g is addressed as ``n_local + g`` (the gathered block is in global order)."""
+def chunk_starts(n_local: int, chunks: int) -> np.ndarray:
+    """Row chunks of the dense plane: ``chunks`` near-equal contiguous pieces of the local rows."""
+    chunks = max(1, min(int(chunks), max(n_local, 1)))
+    return np.array([(n_local * c) // chunks for c in range(chunks + 1)], dtype=np.int64)
+
+
+def dense_columns(plan: HaloPlan, starts: Optional[np.ndarray] = None) -> np.ndarray:
+    """Column indices for the all-gather data plane: own rows stay local, the remote row with
+    global id g = (owner r, local row i) is addressed as ``n_local + pos(g)``.  The local rows
+    are gathered in chunks (``starts``, see :func:`chunk_starts`); chunk c of all ranks lands in
+    one contiguous region ``[world*starts[c], world*starts[c+1])`` ordered by owner, so
+    ``pos = world*starts[c] + r*size_c + (i - starts[c])`` (one chunk: pos = g)."""
+    n = plan.n_local
+    if starts is None:
+        starts = np.array([0, n], dtype=np.int64)
     col = plan.graph.col_idx.astype(np.int64)
-    remote = col >= plan.n_local
+    remote = col >= n
+    g = plan.need_ids[col[remote] - n]
+    r, i = g // max(n, 1), g % max(n, 1)
+    c = np.searchsorted(starts, i, side="right") - 1
+    size = np.diff(starts)[c]
     out = col.copy()
-    out[remote] = plan.n_local + plan.need_ids[col[remote] - plan.n_local]
+    out[remote] = n + plan.world * starts[c] + r * size + (i - starts[c])
     return out.astype(np.uint32)
 
 
@@ -192,22 +208,34 @@ class Partition:
     block contiguously and all-gather it (chosen collectively when the halo is almost
     everything, see :func:`choose_dense`).
 
+    The dense plane moves message rows only (H floats instead of the 3H of K|V|M): the rows are
+    all-gathered in ``chunks`` pieces and K|V of each piece is rebuilt on arrival
+    (``ruvgnn_layer_expand_halo``, the projection's own GEMM, so the bits are the owner's) while
+    the next piece is still on the wire; during that phase the kernels' grids leave ``comm_sms``
+    SMs to the collective.
+
     ``overlap``: the collective is issued asynchronously (NCCL runs it on its own stream) and
     the interior row ranges (:func:`interior_runs`) are aggregated and updated while it is in
     flight; the launching stream then waits for the halo and finishes the boundary ranges.
     Each row sees exactly the same arithmetic either way."""
 
-    def __init__(self, plan: HaloPlan, ctx, dense: bool = False, overlap: bool = True):
+    def __init__(self, plan: HaloPlan, ctx, dense: bool = False, overlap: bool = True, chunks: int = 4,
+                 comm_sms: Optional[int] = None):
         import torch
 
         from .graph import CsrGraph
 
         self.plan, self.ctx, self.dense = plan, ctx, dense
+        import os
+
+        self.comm_sms = int(os.environ.get("RUVGNN_COMM_SMS", "16")) if comm_sms is None else int(comm_sms)
         if dense:
             n_total = int(plan.bounds[-1])
-            g = CsrGraph(plan.graph.row_ptr, dense_columns(plan), plan.graph.edge_w)
+            self.starts = chunk_starts(plan.n_local, chunks)
+            g = CsrGraph(plan.graph.row_ptr, dense_columns(plan, self.starts), plan.graph.edge_w)
             self.graph = g.to_device(ctx, n_cols=plan.n_local + n_total)
-            self.send_idx = torch.arange(plan.n_local, dtype=torch.int32, device="cuda")
+            self.send_idx = torch.zeros(0, dtype=torch.int32, device="cuda")
+            self._mg = None
         else:
             self.graph = plan.graph.to_device(ctx, n_cols=plan.n_local + plan.n_halo)
             self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
@@ -231,7 +259,8 @@ class Partition:
         return float(self._wait_ev[0].elapsed_time(self._wait_ev[1]))
 
     def forward(self, layer, x_dev, out_dev, timing: bool = False):
-        """project -> pack -> all-to-all-v (NCCL) -> gather/aggregate + update.  Enqueue only."""
+        """project -> pack -> exchange (NCCL, asynchronous) || interior rows -> boundary rows.
+        Enqueue only."""
         import ctypes as C
 
         import torch
@@ -241,23 +270,29 @@ class Partition:
         lib, plan, H = _lib.load(), self.plan, layer.hidden_dim
         h = layer._device_layer()
         _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, plan.n_local, C.c_void_p(x_dev.data_ptr())))
-        n_send = int(self.send_idx.numel())
         W = int(lib.ruvgnn_layer_halo_width(h))  # 3H (K|V|M rows) or H (message rows, R=1 layers)
-        if self._send is None or self._send.shape != (n_send, W):
-            self._send = torch.empty((n_send, W), dtype=torch.float32, device=x_dev.device)
-        if n_send:
-            _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
-                                            C.c_void_p(self._send.data_ptr())))
         import torch.distributed as dist
 
-        work = None
+        work, works = None, []
         if self.dense:
-            n_total = int(plan.bounds[-1])
-            if self._halo is None or self._halo.shape != (n_total, W):
-                self._halo = torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
-            work = dist.all_gather_into_tensor(self._halo, self._send, async_op=True)
-            self.bytes_exchanged = (n_total - plan.n_local) * W * 4 * 2
+            n, n_total, P = plan.n_local, int(plan.bounds[-1]), plan.world
+            if self._send is None or self._send.shape != (n, H):
+                self._send = torch.empty((n, H), dtype=torch.float32, device=x_dev.device)
+                self._mg = torch.empty((n_total, H), dtype=torch.float32, device=x_dev.device)
+                # message rows ARE the halo rows when the layer's halo width is H
+                self._halo = self._mg if W == H else torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
+            _lib.check(lib.ruvgnn_layer_messages(self.ctx.handle, h, 0, n, C.c_void_p(self._send.data_ptr())))
+            for c in range(len(self.starts) - 1):
+                a, b = int(self.starts[c]), int(self.starts[c + 1])
+                works.append(dist.all_gather_into_tensor(self._mg[P * a:P * b], self._send[a:b], async_op=True))
+            self.bytes_exchanged = (n_total - n) * H * 4 * 2
         else:
+            n_send = int(self.send_idx.numel())
+            if self._send is None or self._send.shape != (n_send, W):
+                self._send = torch.empty((n_send, W), dtype=torch.float32, device=x_dev.device)
+            if n_send:
+                _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
+                                                C.c_void_p(self._send.data_ptr())))
             if self._halo is None or self._halo.shape != (plan.n_halo, W):
                 self._halo = torch.empty((plan.n_halo, W), dtype=torch.float32, device=x_dev.device)
             if plan.world > 1:
@@ -270,6 +305,9 @@ class Partition:
             _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr),
                                                          a, b, C.c_void_p(out_dev.data_ptr())))
 
+        limited = bool(works or work is not None) and self.comm_sms > 0
+        if limited:  # leave SMs to the collective: persistent grids must not queue behind its blocks
+            _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, -self.comm_sms))
         for a, b in self.interior:  # no remote neighbour: runs while the collective is in flight
             rows(a, b)
         if self._wait_ev is None:
@@ -277,7 +315,19 @@ class Partition:
         self._wait_ev[0].record()
         if work is not None:
             work.wait()  # the launching stream waits for the halo; the host does not block
+        for c, wk in enumerate(works):  # dense plane: rebuild K|V of piece c while piece c+1 is on the wire
+            wk.wait()
+            if W == H:
+                continue
+            a, b = int(self.starts[c]), int(self.starts[c + 1])
+            P, r = plan.world, plan.rank
+            for lo, hi in ((P * a, P * a + r * (b - a)), (P * a + (r + 1) * (b - a), P * b)):  # skip own block
+                if hi > lo:
+                    _lib.check(lib.ruvgnn_layer_expand_halo(self.ctx.handle, h, C.c_void_p(self._mg[lo:hi].data_ptr()),
+                                                            hi - lo, C.c_void_p(self._halo[lo:hi].data_ptr())))
         self._wait_ev[1].record()
+        if limited:
+            _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, 0))
         for a, b in self.boundary:
             rows(a, b)
 

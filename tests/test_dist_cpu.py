@@ -149,3 +149,27 @@ def test_interior_runs_tile_the_local_rows_and_touch_no_halo():
     assert interior0 == [] and boundary0 == [(0, plan0.n_local)]
     few, rest = rvdist.interior_runs(plan0, min_rows=1, max_runs=2)
     assert len(few) <= 2 and sum(b - a for a, b in few + rest) == plan0.n_local
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_dense_columns_address_the_chunked_all_gather_layout(chunks):
+    n_per, world = 1001, 4
+    n = n_per * world
+    g = synth.hnsw_like_graph(n, 8, seed=11, locality=0.0)
+    bounds = rvdist.even_bounds(n, world)
+    starts = rvdist.chunk_starts(n_per, chunks)
+    assert starts[0] == 0 and starts[-1] == n_per and (np.diff(starts) > 0).all()
+    # what the chunked all-gather leaves in the buffer: piece c of every rank, ordered by owner
+    gathered = np.concatenate([np.arange(bounds[r] + starts[c], bounds[r] + starts[c + 1])
+                               for c in range(len(starts) - 1) for r in range(world)])
+    assert gathered.size == n
+    for rank in (0, 2, 3):
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        rows = _slice_rows(g, lo, hi)
+        plan = rvdist.HaloPlan.build(rows, rank, bounds)
+        col = rvdist.dense_columns(plan, starts).astype(np.int64)
+        orig = rows.col_idx.astype(np.int64)
+        local = (orig >= lo) & (orig < hi)
+        assert np.array_equal(col[local], orig[local] - lo)
+        assert (col[~local] >= n_per).all()
+        assert np.array_equal(gathered[col[~local] - n_per], orig[~local])
