@@ -214,9 +214,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        # the collective shares the GPU with the kernels that run under it: cap its blocks at the SMs
-        # the partitioned forward leaves free (ruvector_b200.dist.Partition.comm_sms)
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("RUVGNN_COMM_SMS", "16"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 

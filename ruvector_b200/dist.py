@@ -228,7 +228,10 @@ class Partition:
         self.plan, self.ctx, self.dense = plan, ctx, dense
         import os
 
-        self.comm_sms = int(os.environ.get("RUVGNN_COMM_SMS", "16")) if comm_sms is None else int(comm_sms)
+        # SMs left to the collective while kernels run beside it.  Measured on 2 B200s: 0, 16 and 32 give the
+        # same step time (the GEMMs that run beside the exchange are L2-bandwidth-bound and so is the
+        # collective's copy, so they share that, not SMs) and capping NCCL's blocks costs bandwidth: default 0.
+        self.comm_sms = int(os.environ.get("RUVGNN_COMM_SMS", "0")) if comm_sms is None else int(comm_sms)
         if dense:
             n_total = int(plan.bounds[-1])
             self.starts = chunk_starts(plan.n_local, chunks)
@@ -244,6 +247,23 @@ class Partition:
         self.interior, self.boundary = interior_runs(plan) if overlap else ([], [(0, plan.n_local)] if plan.n_local else [])
         self.interior_rows = sum(b - a for a, b in self.interior)
         self._wait_ev = None
+        self.trace = None  # set to [] to collect (label, event) pairs of the next forward (diagnostics)
+
+    def _mark(self, label):
+        if self.trace is not None:
+            import torch
+
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
+
+    def trace_ms(self):
+        """[(label, ms since the previous mark)] of the traced forward.  Synchronises."""
+        out = []
+        for (_, e0), (label, e1) in zip(self.trace, self.trace[1:]):
+            e1.synchronize()
+            out.append((label, round(float(e0.elapsed_time(e1)), 3)))
+        return out
 
     @classmethod
     def build(cls, local_rows: CsrGraph, rank: int, world: int, n_per_rank: int, ctx, overlap: bool = True) -> "Partition":
@@ -269,7 +289,9 @@ class Partition:
 
         lib, plan, H = _lib.load(), self.plan, layer.hidden_dim
         h = layer._device_layer()
+        self._mark("start")
         _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, plan.n_local, C.c_void_p(x_dev.data_ptr())))
+        self._mark("project")
         W = int(lib.ruvgnn_layer_halo_width(h))  # 3H (K|V|M rows) or H (message rows, R=1 layers)
         import torch.distributed as dist
 
@@ -305,6 +327,7 @@ class Partition:
             _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr),
                                                          a, b, C.c_void_p(out_dev.data_ptr())))
 
+        self._mark("pack")
         limited = bool(works or work is not None) and self.comm_sms > 0
         if limited:  # leave SMs to the collective: persistent grids must not queue behind its blocks
             _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, -self.comm_sms))
@@ -317,6 +340,7 @@ class Partition:
             work.wait()  # the launching stream waits for the halo; the host does not block
         for c, wk in enumerate(works):  # dense plane: rebuild K|V of piece c while piece c+1 is on the wire
             wk.wait()
+            self._mark(f"wait{c}")
             if W == H:
                 continue
             a, b = int(self.starts[c]), int(self.starts[c + 1])
@@ -325,11 +349,13 @@ class Partition:
                 if hi > lo:
                     _lib.check(lib.ruvgnn_layer_expand_halo(self.ctx.handle, h, C.c_void_p(self._mg[lo:hi].data_ptr()),
                                                             hi - lo, C.c_void_p(self._halo[lo:hi].data_ptr())))
+            self._mark(f"expand{c}")
         self._wait_ev[1].record()
         if limited:
             _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, 0))
         for a, b in self.boundary:
             rows(a, b)
+        self._mark("boundary")
 
     def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray):
         """Host buffers in, host buffers out (H2D / D2H inside): the e2e leg of bench.py."""

@@ -24,7 +24,6 @@ from ruvector_b200.graph import CsrGraph  # noqa: E402
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("RUVGNN_COMM_SMS", "16"))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
     for (n, d, heads, m, mode, loc) in [(6000, 128, 4, 16, rv.MODE_FP32_SIMT, 0.0), (5000, 384, 8, 16, rv.MODE_FP32_TC, 0.5),
