@@ -48,6 +48,11 @@ struct ruvgnn_ctx {
   // exchange in the partitioned path), 3 after gather, 4 after update, 5 after d2h
   static constexpr int kRing = 32;
   cudaEvent_t ring[kRing][7] = {};
+  // (start, end) event pairs around every K-agg launch of a slot (a forward may run K-agg once
+  // per row block / row range); created on first use
+  std::vector<cudaEvent_t> agg_ev[kRing];
+  uint32_t agg_used[kRing] = {};
+  int cur_slot = 0;
   bool timing_on = false;  // ruvgnn_ctx_set_timing: also time project / aggregate_update
   // host-buffer forward: copy streams + per-block events for the H2D | compute | D2H pipeline
   static constexpr int kMaxBlocks = 16;
@@ -132,10 +137,28 @@ struct DeviceGuard {
 
 // floats per node of activation workspace: R=3: P(4H) OA(2H) T0..T3(4H); R=1: M(H) Qt(hH)
 // SA((h+1)H) T0..T3(4H)
-uint32_t ws_units(const ruvgnn_layer *L) { return L->r1 ? 2 * L->heads + 6 : 10; }
+// Activation workspace.  Per node (kept for the whole forward, the gather reads them at arbitrary
+// rows): P[n][4H] = Q|K|V|M (R = 3) or M[n][H] + Qt[n][hH] (R = 1).  Per row block of at most
+// upd_block() rows (reused block after block by K-agg -> K-upd): OA[B][2H] or SA[B][(h+1)H], and
+// T0..T3[B][H].  1M nodes x 384: 6.1 + 9.2 GB; 10M nodes x 128 (R = 1, 4 heads): 25.6 + 4.8 GB
+// instead of 71.7 GB with everything per node.
+uint64_t upd_block() {
+  static uint64_t b = 0;
+  if (!b) {
+    const char *e = getenv("RUVGNN_UPD_BLOCK");  // tests shrink it to exercise the block loop
+    const long long v = e ? atoll(e) : 0;
+    b = v > 0 ? (uint64_t)v : (uint64_t)1 << 20;
+  }
+  return b;
+}
+uint32_t ws_node_units(const ruvgnn_layer *L) { return L->r1 ? 1 + L->heads : 4; }
+uint32_t ws_block_units(const ruvgnn_layer *L) { return L->r1 ? L->heads + 5 : 6; }
+size_t ws_floats_needed(const ruvgnn_layer *L, uint64_t n) {
+  const uint64_t B = n < upd_block() ? n : upd_block();
+  return (size_t)n * L->H * ws_node_units(L) + (size_t)B * L->H * ws_block_units(L) + 64;
+}
 
-int32_t ensure_ws(ruvgnn_ctx *c, uint64_t n, uint32_t H, uint32_t units = 10) {
-  const size_t need = (size_t)n * H * units + 64;
+int32_t ensure_ws_floats(ruvgnn_ctx *c, size_t need) {
   if (need <= c->ws_floats) return RUVGNN_OK;
   if (c->ws) {
     RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -146,6 +169,9 @@ int32_t ensure_ws(ruvgnn_ctx *c, uint64_t n, uint32_t H, uint32_t units = 10) {
   RUVGNN_CUDA_TRY(cudaMalloc(&c->ws, need * sizeof(float)));
   c->ws_floats = need;
   return RUVGNN_OK;
+}
+int32_t ensure_ws(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
+  return ensure_ws_floats(c, ws_floats_needed(L, n));
 }
 
 int32_t ensure_stage(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
@@ -172,14 +198,22 @@ struct Ws {
   // R = 1 only
   float *Qt, *SA;
 };
+void begin_timing_slot(ruvgnn_ctx *c) {
+  c->cur_slot = (int)(c->ring_count % ruvgnn_ctx::kRing);
+  c->ev = c->ring[c->cur_slot];
+  c->agg_used[c->cur_slot] = 0;
+  ++c->ring_count;
+}
+
 Ws carve(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
   const uint32_t H = L->H;
+  const uint64_t B = n < upd_block() ? n : upd_block();
   Ws w{};
   if (!L->r1) {
     w.P = c->ws;
     w.ldp = 4 * (int64_t)H;
-    w.OA = w.P + (size_t)n * 4 * H;
-    w.T0 = w.OA + (size_t)n * 2 * H;
+    w.OA = w.P + (size_t)n * 4 * H;  // block-local from here on
+    w.T0 = w.OA + (size_t)B * 2 * H;
     w.m = w.P + 3 * H;
     w.ldm = w.ldp;
     w.halo_src = w.P + H;
@@ -189,14 +223,14 @@ Ws carve(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
     w.m = c->ws;
     w.ldm = H;
     w.Qt = w.m + (size_t)n * H;
-    w.SA = w.Qt + (size_t)n * h * H;
-    w.T0 = w.SA + (size_t)n * (h + 1) * H;
+    w.SA = w.Qt + (size_t)n * h * H;  // block-local from here on
+    w.T0 = w.SA + (size_t)B * (h + 1) * H;
     w.halo_src = w.m;
     w.halo_w = H;
   }
-  w.T1 = w.T0 + (size_t)n * H;
-  w.T2 = w.T1 + (size_t)n * H;
-  w.T3 = w.T2 + (size_t)n * H;
+  w.T1 = w.T0 + (size_t)B * H;
+  w.T2 = w.T1 + (size_t)B * H;
+  w.T3 = w.T2 + (size_t)B * H;
   return w;
 }
 
@@ -218,7 +252,7 @@ int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKin
 int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev,
                         uint64_t rb, uint64_t re) {
   const uint32_t H = L->H, D = L->D;
-  int32_t rc = ensure_ws(c, n, H, ws_units(L));
+  int32_t rc = ensure_ws(c, L, n);
   if (rc) return rc;
   if (re <= rb) return RUVGNN_OK;
   Ws w = carve(c, L, n);
@@ -262,14 +296,34 @@ int32_t do_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float
 
 // Phase B: K-agg over rows [rb,re), then K-upd (out-proj + combine + W_agg, GRU,
 // dropout scale, LayerNorm; layer.rs:156-159,407-417).
-int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
-                            const float *halo, uint64_t rb, uint64_t re, float *out_dev,
-                            bool stage_events = true) {
+int32_t aggregate_update_block(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
+                               const float *halo, uint64_t rb, uint64_t re, float *out_dev,
+                               bool stage_events) {
   const uint32_t H = L->H;
   const uint64_t n = c->proj_rows;
-  if (re <= rb) return RUVGNN_OK;
   Ws w = carve(c, L, n);
-  if (c->timing_valid && stage_events) cudaEventRecord(c->ev[6], c->stream);
+  // OA / SA / T0..T3 hold rows [rb, re) only: row r of the block lives at index r - rb.  The
+  // kernels and GEMM arguments below index them by the node's row, so shift the bases once.
+  w.OA -= (ptrdiff_t)(rb * 2 * H);
+  if (L->r1) w.SA -= (ptrdiff_t)(rb * (uint64_t)(L->heads + 1) * H);
+  w.T0 -= (ptrdiff_t)(rb * H);
+  w.T1 -= (ptrdiff_t)(rb * H);
+  w.T2 -= (ptrdiff_t)(rb * H);
+  w.T3 -= (ptrdiff_t)(rb * H);
+  cudaEvent_t agg_end = nullptr;
+  if (c->timing_valid && stage_events) {
+    std::vector<cudaEvent_t> &pool = c->agg_ev[c->cur_slot];
+    uint32_t &used = c->agg_used[c->cur_slot];
+    while (pool.size() < 2 * (size_t)(used + 1)) {
+      cudaEvent_t e;
+      RUVGNN_CUDA_TRY(cudaEventCreate(&e));
+      pool.push_back(e);
+    }
+    if (used == 0) cudaEventRecord(c->ev[6], c->stream);
+    cudaEventRecord(pool[2 * used], c->stream);
+    agg_end = pool[2 * used + 1];
+    ++used;
+  }
   if (!L->r1) {
     GatherArgs ga;
     ga.P = w.P;
@@ -303,7 +357,10 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
     ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
     RUVGNN_CUDA_TRY(launch_gather_r1(ga, c->sm_count, c->stream, &c->launches));
   }
-  if (c->timing_valid && stage_events) cudaEventRecord(c->ev[3], c->stream);
+  if (agg_end) {
+    cudaEventRecord(agg_end, c->stream);
+    cudaEventRecord(c->ev[3], c->stream);
+  }
 
   const int64_t rows = (int64_t)(re - rb);
   const float *m = w.m + rb * w.ldm;
@@ -368,6 +425,19 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
   ln.row_begin = rb; ln.row_end = re;
   ln.H = H; ln.P = L->ord.P;
   RUVGNN_CUDA_TRY(launch_layernorm(ln, c->stream, &c->launches));
+  return RUVGNN_OK;
+}
+
+// Phase B over rows [rb, re): one K-agg -> K-upd pass per block of at most upd_block() rows.
+int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
+                            const float *halo, uint64_t rb, uint64_t re, float *out_dev,
+                            bool stage_events = true) {
+  const uint64_t B = upd_block();
+  for (uint64_t b0 = rb; b0 < re; b0 += B) {
+    const uint64_t b1 = b0 + B < re ? b0 + B : re;
+    int32_t rc = aggregate_update_block(c, L, G, halo, b0, b1, out_dev, stage_events);
+    if (rc) return rc;
+  }
   return RUVGNN_OK;
 }
 
@@ -603,6 +673,8 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
   for (auto &slot : c->ring)
     for (auto &ev : slot)
       if (ev) cudaEventDestroy(ev);
+  for (auto &pool : c->agg_ev)
+    for (auto &ev : pool) cudaEventDestroy(ev);
   for (auto &ev : c->ev_in)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->ev_out)
@@ -648,8 +720,17 @@ int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms6) {
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&h2d, e[0], e[1]));
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&proj, e[1], e[2]));
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&xchg, e[2], e[6]));
-    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[6], e[3]));
-    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&upd, e[3], e[4]));
+    // K-agg = sum over its launches (one per row block / row range); K-upd = the rest of phase B
+    float phase_b;
+    RUVGNN_CUDA_TRY(cudaEventElapsedTime(&phase_b, e[6], e[4]));
+    agg = 0.f;
+    for (uint32_t k = 0; k < c->agg_used[sl]; ++k) {
+      float t;
+      RUVGNN_CUDA_TRY(cudaEventElapsedTime(&t, c->agg_ev[sl][2 * k], c->agg_ev[sl][2 * k + 1]));
+      agg += t;
+    }
+    if (c->agg_used[sl] == 0) RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[6], e[3]));
+    upd = phase_b - agg;
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, e[4], e[5]));
     acc[0] += proj; acc[1] += agg; acc[2] += upd; acc[3] += h2d; acc[4] += d2h; acc[5] += xchg;
   }
@@ -884,11 +965,10 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   } else if (x == out) {
     return fail(RUVGNN_ERR_INVALID_INPUT, "out must not alias x (Jacobi update)");
   }
-  if ((rc = ensure_ws(c, n, L->H, ws_units(L)))) return rc;
+  if ((rc = ensure_ws(c, L, n))) return rc;
   if (timing) {
     c->timing_valid = true;
-    c->ev = c->ring[c->ring_count % ruvgnn_ctx::kRing];
-    ++c->ring_count;
+    begin_timing_slot(c);
     cudaEventRecord(c->ev[0], c->stream);
   }
   if (dev_ptrs) {
@@ -977,11 +1057,12 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
   const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
   c->timing_valid = false;
   int32_t rc;
-  uint32_t maxH = 0;
-  for (uint32_t l = 0; l < n_layers; ++l) maxH = layers[l]->H > maxH ? layers[l]->H : maxH;
-  uint32_t max_units = 10;
-  for (uint32_t l = 0; l < n_layers; ++l) max_units = ws_units(layers[l]) > max_units ? ws_units(layers[l]) : max_units;
-  if ((rc = ensure_ws(c, n, maxH, max_units))) return rc;
+  size_t ws_need = 0;
+  for (uint32_t l = 0; l < n_layers; ++l) {
+    const size_t f = ws_floats_needed(layers[l], n);
+    ws_need = f > ws_need ? f : ws_need;
+  }
+  if ((rc = ensure_ws_floats(c, ws_need))) return rc;
   const float *cur = x;
   if (!dev_ptrs) {
     if ((rc = ensure_stage(c, &c->x_stage, &c->x_stage_floats, (size_t)n * layers[0]->D))) return rc;
@@ -1063,8 +1144,7 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = c->timing_on;
   if (c->timing_on) {
-    c->ev = c->ring[c->ring_count % ruvgnn_ctx::kRing];
-    ++c->ring_count;
+    begin_timing_slot(c);
     cudaEventRecord(c->ev[0], c->stream);
     cudaEventRecord(c->ev[1], c->stream);
   }

@@ -359,3 +359,29 @@ def test_seeded_fuzz_over_shapes_degrees_and_modes(oracle, ctx):
                 continue
             rel = np.linalg.norm(out - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-6)
             assert rel.max() <= 1e-4, (case, n, d, hdim, heads, mode, float(rel.max()))
+
+
+def test_row_block_loop_changes_no_bit(tmp_path):
+    """K-agg -> K-upd runs per block of at most 2^20 rows on block-sized buffers; with a 777-row block
+    (ragged last block, many blocks) every output must equal the single-block run bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    outs = []
+    for block in (None, "777"):
+        env = dict(os.environ)
+        env.pop("RUVGNN_UPD_BLOCK", None)
+        if block:
+            env["RUVGNN_UPD_BLOCK"] = block
+        path = tmp_path / f"out_{block}.npz"
+        res = subprocess.run([sys.executable, str(root / "scripts" / "block_loop_check.py"), str(path)], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(np.load(path))
+    assert set(outs[0].files) == set(outs[1].files) and len(outs[0].files) == 7
+    for k in outs[0].files:
+        assert np.isfinite(outs[0][k]).all()
+        assert np.array_equal(outs[0][k], outs[1][k]), k
