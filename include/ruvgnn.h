@@ -232,6 +232,11 @@ int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *ctx, const float *queries, uint6
  * that peers need. */
 int32_t ruvgnn_layer_project(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, uint64_t n_local,
                              const float *x_dev);
+/* Same for rows [row_begin, row_end) only (x_dev is still the base of all n_local rows): lets a
+ * caller project row blocks as their host-to-device copies land.  Every row must be projected
+ * before ruvgnn_halo_pack / ruvgnn_layer_messages / ruvgnn_layer_aggregate_update. */
+int32_t ruvgnn_layer_project_rows(ruvgnn_ctx *ctx, const ruvgnn_layer *layer, uint64_t n_local,
+                                  const float *x_dev, uint64_t row_begin, uint64_t row_end);
 /* Floats per halo row of this layer: 3*hidden_dim (K|V|M rows) or hidden_dim (message row
  * only, when the layer runs the single-row gather formulation: hidden_dim == 128, <= 4 heads). */
 uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *layer);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "ruvgnn_differentiable_search": (C.c_int32, [_vp, c_float_p, C.c_uint64, c_float_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, _u32p, c_float_p, _u32p, C.c_uint32]),
     "ruvgnn_hierarchical_forward": (C.c_int32, [_vp, c_float_p, C.c_uint64, C.c_uint32, C.POINTER(c_float_p), _u64p, _u32p, C.POINTER(_vp), C.c_uint32, c_float_p, C.c_uint32, _u32p]),
     "ruvgnn_layer_project": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
+    "ruvgnn_layer_project_rows": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64]),
     "ruvgnn_layer_halo_width": (C.c_uint32, [_vp]),
     "ruvgnn_halo_pack": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_messages": (C.c_int32, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),

@@ -1153,6 +1153,24 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   return rc;
 }
 
+int32_t ruvgnn_layer_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_local,
+                                  const float *x_dev, uint64_t row_begin, uint64_t row_end) {
+  if (!c || !L || !x_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
+  if (row_end > n_local || row_begin > row_end)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "row range out of bounds");
+  DeviceGuard dg(c->device);
+  if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  c->timing_valid = c->timing_on;
+  if (c->timing_on && row_begin == 0) {
+    begin_timing_slot(c);
+    cudaEventRecord(c->ev[0], c->stream);
+    cudaEventRecord(c->ev[1], c->stream);
+  }
+  int32_t rc = do_project_rows(c, L, n_local, x_dev, row_begin, row_end);
+  if (c->timing_on) cudaEventRecord(c->ev[2], c->stream);
+  return rc;
+}
+
 uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *L) {
   if (!L) return 0;
   return L->r1 ? L->H : 3 * L->H;

@@ -238,11 +238,11 @@ class Partition:
             g = CsrGraph(plan.graph.row_ptr, dense_columns(plan, self.starts), plan.graph.edge_w)
             self.graph = g.to_device(ctx, n_cols=plan.n_local + n_total)
             self.send_idx = torch.zeros(0, dtype=torch.int32, device="cuda")
-            self._mg = None
         else:
             self.graph = plan.graph.to_device(ctx, n_cols=plan.n_local + plan.n_halo)
             self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
-        self._send = self._halo = self._x = self._out = None
+        self._send = self._halo = self._x = self._out = self._s_in = self._s_out = None
+        self._ring = []
         self.bytes_exchanged = 0
         self.interior, self.boundary = interior_runs(plan) if overlap else ([], [(0, plan.n_local)] if plan.n_local else [])
         self.interior_rows = sum(b - a for a, b in self.interior)
@@ -281,32 +281,68 @@ class Partition:
     def forward(self, layer, x_dev, out_dev, timing: bool = False):
         """project -> pack -> exchange (NCCL, asynchronous) || interior rows -> boundary rows.
         Enqueue only."""
+        self._forward(layer, x_dev, out_dev)
+
+    def _forward(self, layer, x_dev, out_dev, x_host=None, out_host=None, blocks: int = 8):
+        """Device buffers, or (``x_host`` / ``out_host`` given, pinned) the host-buffer pipeline: X is
+        copied in row blocks on a copy stream and each block is projected as it lands; each finished
+        row range of the output is copied back on a second copy stream while the next range computes."""
         import ctypes as C
 
         import torch
+        import torch.distributed as dist
 
         from . import _lib
 
         lib, plan, H = _lib.load(), self.plan, layer.hidden_dim
         h = layer._device_layer()
+        n = plan.n_local
+        main = torch.cuda.current_stream()
         self._mark("start")
-        _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, plan.n_local, C.c_void_p(x_dev.data_ptr())))
+        if x_host is None:
+            _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, n, C.c_void_p(x_dev.data_ptr())))
+        else:
+            if self._s_in is None:
+                self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            self._s_in.wait_stream(main)
+            self._s_out.wait_stream(main)
+            edges = [(n * b) // blocks for b in range(blocks + 1)]
+            landed = []
+            with torch.cuda.stream(self._s_in):
+                for a, b in zip(edges, edges[1:]):
+                    if b > a:
+                        x_dev[a:b].copy_(x_host[a:b], non_blocking=True)
+                        landed.append((a, b, self._s_in.record_event()))
+            for a, b, ev in landed:
+                main.wait_event(ev)
+                _lib.check(lib.ruvgnn_layer_project_rows(self.ctx.handle, h, n, C.c_void_p(x_dev.data_ptr()), a, b))
         self._mark("project")
         W = int(lib.ruvgnn_layer_halo_width(h))  # 3H (K|V|M rows) or H (message rows, R=1 layers)
-        import torch.distributed as dist
 
-        work, works = None, []
+        work, works = None, {}
         if self.dense:
-            n, n_total, P = plan.n_local, int(plan.bounds[-1]), plan.world
+            n_total, P = int(plan.bounds[-1]), plan.world
+            nchunks = len(self.starts) - 1
             if self._send is None or self._send.shape != (n, H):
                 self._send = torch.empty((n, H), dtype=torch.float32, device=x_dev.device)
-                self._mg = torch.empty((n_total, H), dtype=torch.float32, device=x_dev.device)
-                # message rows ARE the halo rows when the layer's halo width is H
-                self._halo = self._mg if W == H else torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
+                self._halo = torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
+                # K|V|M halo rows: the gathered message rows pass through a 2-deep ring of chunk
+                # buffers; message-row halos (W == H) are gathered straight into place
+                big = int(np.diff(self.starts).max())
+                self._ring = [] if W == H else [torch.empty((P * big, H), dtype=torch.float32, device=x_dev.device)
+                                                for _ in range(min(2, nchunks))]
             _lib.check(lib.ruvgnn_layer_messages(self.ctx.handle, h, 0, n, C.c_void_p(self._send.data_ptr())))
-            for c in range(len(self.starts) - 1):
+
+            def landing(c):
                 a, b = int(self.starts[c]), int(self.starts[c + 1])
-                works.append(dist.all_gather_into_tensor(self._mg[P * a:P * b], self._send[a:b], async_op=True))
+                return self._halo[P * a:P * b] if W == H else self._ring[c % 2][:P * (b - a)]
+
+            def issue(c):  # the collective starts after everything enqueued so far on this stream
+                a, b = int(self.starts[c]), int(self.starts[c + 1])
+                works[c] = dist.all_gather_into_tensor(landing(c), self._send[a:b], async_op=True)
+
+            for c in range(nchunks if W == H else min(2, nchunks)):
+                issue(c)
             self.bytes_exchanged = (n_total - n) * H * 4 * 2
         else:
             n_send = int(self.send_idx.numel())
@@ -322,10 +358,17 @@ class Partition:
                                               plan.send_counts.tolist(), async_op=True)
             self.bytes_exchanged = (n_send + plan.n_halo) * W * 4
         halo_ptr = self._halo.data_ptr() if (plan.n_halo or self.dense) else None
+        step = max((n + blocks - 1) // blocks, 1) if out_host is not None else max(n, 1)
 
         def rows(a, b):
-            _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle, C.c_void_p(halo_ptr),
-                                                         a, b, C.c_void_p(out_dev.data_ptr())))
+            for a0 in range(a, b, step):  # host pipeline: hand finished sub-ranges to the copy-out stream
+                b0 = min(a0 + step, b)
+                _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle,
+                                                             C.c_void_p(halo_ptr), a0, b0, C.c_void_p(out_dev.data_ptr())))
+                if out_host is not None:
+                    self._s_out.wait_event(main.record_event())
+                    with torch.cuda.stream(self._s_out):
+                        out_host[a0:b0].copy_(out_dev[a0:b0], non_blocking=True)
 
         self._mark("pack")
         limited = bool(works or work is not None) and self.comm_sms > 0
@@ -338,34 +381,39 @@ class Partition:
         self._wait_ev[0].record()
         if work is not None:
             work.wait()  # the launching stream waits for the halo; the host does not block
-        for c, wk in enumerate(works):  # dense plane: rebuild K|V of piece c while piece c+1 is on the wire
-            wk.wait()
-            self._mark(f"wait{c}")
-            if W == H:
-                continue
-            a, b = int(self.starts[c]), int(self.starts[c + 1])
+        if self.dense:  # rebuild K|V of chunk c while chunk c+1 is on the wire
             P, r = plan.world, plan.rank
-            for lo, hi in ((P * a, P * a + r * (b - a)), (P * a + (r + 1) * (b - a), P * b)):  # skip own block
-                if hi > lo:
-                    _lib.check(lib.ruvgnn_layer_expand_halo(self.ctx.handle, h, C.c_void_p(self._mg[lo:hi].data_ptr()),
-                                                            hi - lo, C.c_void_p(self._halo[lo:hi].data_ptr())))
-            self._mark(f"expand{c}")
+            for c in range(nchunks):
+                works[c].wait()
+                self._mark(f"wait{c}")
+                if W == H:
+                    continue
+                a, b = int(self.starts[c]), int(self.starts[c + 1])
+                src, dst = landing(c), self._halo[P * a:P * b]
+                for lo, hi in ((0, r * (b - a)), ((r + 1) * (b - a), P * (b - a))):  # skip own block
+                    if hi > lo:
+                        _lib.check(lib.ruvgnn_layer_expand_halo(self.ctx.handle, h, C.c_void_p(src[lo:hi].data_ptr()),
+                                                                hi - lo, C.c_void_p(dst[lo:hi].data_ptr())))
+                self._mark(f"expand{c}")
+                if c + 2 < nchunks:
+                    issue(c + 2)  # reuses this chunk's ring buffer: ordered after the rebuild just enqueued
         self._wait_ev[1].record()
         if limited:
             _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, 0))
         for a, b in self.boundary:
             rows(a, b)
         self._mark("boundary")
+        if out_host is not None:
+            main.wait_stream(self._s_out)
 
     def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray):
-        """Host buffers in, host buffers out (H2D / D2H inside): the e2e leg of bench.py."""
+        """Host buffers in, host buffers out (H2D / D2H inside, pipelined against the projection and the
+        update when the buffers are pinned): the e2e leg of bench.py.  Blocks until the output is there."""
         import torch
 
         xt, ot = torch.from_numpy(x_np), torch.from_numpy(out_np)
         if self._x is None or self._x.shape != xt.shape:
             self._x = torch.empty(xt.shape, dtype=torch.float32, device="cuda")
             self._out = torch.empty(ot.shape, dtype=torch.float32, device="cuda")
-        self._x.copy_(xt, non_blocking=True)
-        self.forward(layer, self._x, self._out)
-        ot.copy_(self._out, non_blocking=True)
+        self._forward(layer, self._x, self._out, x_host=xt, out_host=ot)
         torch.cuda.current_stream().synchronize()
