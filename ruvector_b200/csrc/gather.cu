@@ -363,6 +363,159 @@ __global__ void __launch_bounds__(128) gather_r1_kernel(GatherR1Args a, float sc
   }
 }
 
+// Sum each of the N per-lane partials over the 32 lanes; lane L returns the total of value
+// index L / (32 / N) (halving butterfly as above, without the final broadcast).
+template <int N>
+__device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = up ? v[i + n / 2] : v[i];
+      const float send = up ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// Halving butterfly without selects: the caller stores the partial of value index j at
+// position j ^ id, id = lane / (32 / N).  Every lane then keeps v[i] and sends v[i + n/2]; lane
+// L returns the total of value index id(L).
+template <int N>
+__device__ __forceinline__ float reduce_scatter_xor(float (&v)[N]) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i + n / 2], off);
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// R = 1, batched: 8 edges per step.  The 8 x HEADS scores of a step are reduced together (one
+// halving butterfly leaves ONE (edge, head) total per lane: edge slot = lane / 4, head =
+// (lane % 4) / (4 / HEADS)), so the softmax bookkeeping -- running maximum, exp2, normaliser --
+// is one instruction per step instead of one per edge and head; the weights are then broadcast
+// back for the accumulation.
+// Lane-permuted slots: lane L keeps in slot (u, g) the row of edge u ^ (L / 4) and the query /
+// accumulator of head g ^ head(L).  That is the layout the select-free butterfly wants, and every
+// broadcast becomes an xor-shuffle with a compile-time lane mask; the rows are still read as
+// 128-bit loads of the lane's own 4 columns.
+template <int HEADS, bool HALO>
+__global__ void __launch_bounds__(32) gather_r1_batched_kernel(GatherR1Args a, float scale_log2) {
+  constexpr int H = 128, EB = 8, N = EB * HEADS, REP = 32 / N;
+  // ONE warp per block: the node, its row bounds and every loop trip count then derive from
+  // blockIdx, which the compiler knows to be warp-uniform -- the shuffles compile to bare SHFL
+  // (with 4 warps per block each one sat in a WARPSYNC / ENDCOLLECTIVE region).
+  const int lane = threadIdx.x;
+  const uint64_t warp = blockIdx.x;
+  const uint64_t nwarps = gridDim.x;
+  const int my_slot = lane >> 2;               // edge slot of the (edge, head) pair this lane owns
+  const int my_head = (lane / REP) % HEADS;    // and its head
+  for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
+    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    float4 *srow = reinterpret_cast<float4 *>(a.sa + node * (uint64_t)((HEADS + 1) * H));
+    if (beg == end) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g <= HEADS; ++g) srow[g * 32 + lane] = zero;
+      continue;
+    }
+    const float4 *qrow = reinterpret_cast<const float4 *>(a.Qt + node * (uint64_t)(HEADS * H));
+    float4 qt[HEADS], S[HEADS];  // slot g: head g ^ my_head
+#pragma unroll
+    for (int g = 0; g < HEADS; ++g) {
+      const float4 q = ldg4(qrow + (g ^ my_head) * 32 + lane);
+      qt[g] = make_float4(q.x * scale_log2, q.y * scale_log2, q.z * scale_log2, q.w * scale_log2);
+      S[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f);
+    float mx = -INFINITY, lsum = 0.f;  // of my head / my (edge slot, head) pair
+    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
+    for (uint64_t c = beg; c < end; c += 32) {
+      const uint64_t e = c + lane;
+      const uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      const float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
+      const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
+      for (int jj = 0; jj < cnt; jj += EB) {
+        float4 r[EB];  // slot u: edge jj + (u ^ my_slot)
+        float w[EB];
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          // slots beyond the row re-read its last edge (score masked below, weight 0)
+          const int src = jj + (u ^ my_slot);
+          const uint32_t col = __shfl_sync(0xffffffffu, my_col, src < cnt ? src : cnt - 1);
+          w[u] = __shfl_sync(0xffffffffu, my_w, src);
+          const float4 *row;
+          if (HALO)
+            row = (uint64_t)col < a.n_local
+                      ? reinterpret_cast<const float4 *>(a.M + (uint64_t)col * a.ldm)
+                      : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * H);
+          else
+            row = reinterpret_cast<const float4 *>(a.M + (uint64_t)col * a.ldm);
+          r[u] = ldg4(row + lane);
+        }
+        float s[N];  // position u * HEADS + g holds the partial of edge slot u ^ my_slot, head g ^ my_head
+#pragma unroll
+        for (int u = 0; u < EB; ++u)
+#pragma unroll
+          for (int g = 0; g < HEADS; ++g)
+            s[u * HEADS + g] = fmaf(qt[g].x, r[u].x, fmaf(qt[g].y, r[u].y, fmaf(qt[g].z, r[u].z, qt[g].w * r[u].w)));
+        float t = reduce_scatter_xor<N>(s);  // log2-unit score of (edge jj + my_slot, my_head)
+        if (jj + my_slot >= cnt) t = -INFINITY;
+        float bm = t;  // maximum of the step per head: lanes of one head differ in bits 2..4
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+        const float nm = fmaxf(mx, bm);  // finite: every step holds at least one edge
+        const float p = ex2_approx(t - nm);
+        const float corr = ex2_approx(mx - nm);  // first step: mx = -inf, corr = 0 (S, lsum are 0)
+        mx = nm;
+        lsum = fmaf(lsum, corr, p);
+#pragma unroll
+        for (int g = 0; g < HEADS; ++g) {
+          const float cg = g ? __shfl_xor_sync(0xffffffffu, corr, g * REP) : corr;
+          S[g].x *= cg; S[g].y *= cg; S[g].z *= cg; S[g].w *= cg;
+        }
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+#pragma unroll
+          for (int g = 0; g < HEADS; ++g) {
+            const float pug = (u | g) ? __shfl_xor_sync(0xffffffffu, p, (u * HEADS + g) * REP) : p;
+            S[g].x = fmaf(pug, r[u].x, S[g].x);
+            S[g].y = fmaf(pug, r[u].y, S[g].y);
+            S[g].z = fmaf(pug, r[u].z, S[g].z);
+            S[g].w = fmaf(pug, r[u].w, S[g].w);
+          }
+          ag.x = fmaf(w[u], r[u].x, ag.x);
+          ag.y = fmaf(w[u], r[u].y, ag.y);
+          ag.z = fmaf(w[u], r[u].z, ag.z);
+          ag.w = fmaf(w[u], r[u].w, ag.w);
+        }
+      }
+    }
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);  // normaliser of my head: sum over the edge slots
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+#pragma unroll
+    for (int g = 0; g < HEADS; ++g) {
+      const float lg = g ? __shfl_xor_sync(0xffffffffu, lsum, g * REP) : lsum;
+      const float inv_l = 1.0f / fmaxf(lg, 1e-10f);
+      srow[(g ^ my_head) * 32 + lane] = make_float4(S[g].x * inv_l, S[g].y * inv_l, S[g].z * inv_l, S[g].w * inv_l);
+    }
+    srow[HEADS * 32 + lane] = ag;
+  }
+}
+
 template <int HEADS>
 cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, cudaStream_t s) {
   const uint64_t rows = a.row_end - a.row_begin;
@@ -370,6 +523,22 @@ cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, c
   uint64_t blocks = (rows + wpb - 1) / wpb;
   const uint64_t cap = (uint64_t)sm_count * 16;
   if (blocks > cap) blocks = cap;
+  // RUVGNN_R1_BATCH=0 keeps the edge-at-a-time kernel (A/B runs)
+  static int batched = -1;
+  if (batched < 0) {
+    const char *e = getenv("RUVGNN_R1_BATCH");
+    batched = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if constexpr (HEADS <= 4) {
+    if (batched) {
+      uint64_t warps = rows < (uint64_t)sm_count * 64 ? rows : (uint64_t)sm_count * 64;
+      if (a.halo)
+        gather_r1_batched_kernel<HEADS, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+      else
+        gather_r1_batched_kernel<HEADS, false><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+      return cudaGetLastError();
+    }
+  }
   gather_r1_kernel<HEADS, (HEADS <= 4 ? 8 : 4)><<<(unsigned)blocks, 32 * wpb, 0, s>>>(a, scale_log2);
   return cudaGetLastError();
 }
