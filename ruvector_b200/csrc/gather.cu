@@ -410,8 +410,11 @@ __device__ __forceinline__ float reduce_scatter_xor(float (&v)[N]) {
 // accumulator of head g ^ head(L).  That is the layout the select-free butterfly wants, and every
 // broadcast becomes an xor-shuffle with a compile-time lane mask; the rows are still read as
 // 128-bit loads of the lane's own 4 columns.
+// Register budget: 16 resident warps per SM (128 registers).  Measured at 4M nodes: cutting it for 20 / 24
+// warps (96 / 80 registers, small spills) is slower (24.8 / 28.3 vs 23.8 ms), and so is requesting the
+// next step's rows one step ahead (167 registers, 12 warps: 26.6 ms).
 template <int HEADS, bool HALO>
-__global__ void __launch_bounds__(32) gather_r1_batched_kernel(GatherR1Args a, float scale_log2) {
+__global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args a, float scale_log2) {
   constexpr int H = 128, EB = 8, N = EB * HEADS, REP = 32 / N;
   // ONE warp per block: the node, its row bounds and every loop trip count then derive from
   // blockIdx, which the compiler knows to be warp-uniform -- the shuffles compile to bare SHFL
@@ -448,13 +451,11 @@ __global__ void __launch_bounds__(32) gather_r1_batched_kernel(GatherR1Args a, f
       const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
       for (int jj = 0; jj < cnt; jj += EB) {
         float4 r[EB];  // slot u: edge jj + (u ^ my_slot)
-        float w[EB];
 #pragma unroll
         for (int u = 0; u < EB; ++u) {
           // slots beyond the row re-read its last edge (score masked below, weight 0)
           const int src = jj + (u ^ my_slot);
           const uint32_t col = __shfl_sync(0xffffffffu, my_col, src < cnt ? src : cnt - 1);
-          w[u] = __shfl_sync(0xffffffffu, my_w, src);
           const float4 *row;
           if (HALO)
             row = (uint64_t)col < a.n_local
@@ -496,10 +497,11 @@ __global__ void __launch_bounds__(32) gather_r1_batched_kernel(GatherR1Args a, f
             S[g].z = fmaf(pug, r[u].z, S[g].z);
             S[g].w = fmaf(pug, r[u].w, S[g].w);
           }
-          ag.x = fmaf(w[u], r[u].x, ag.x);
-          ag.y = fmaf(w[u], r[u].y, ag.y);
-          ag.z = fmaf(w[u], r[u].z, ag.z);
-          ag.w = fmaf(w[u], r[u].w, ag.w);
+          const float w = __shfl_sync(0xffffffffu, my_w, jj + (u ^ my_slot));  // 0 beyond the row
+          ag.x = fmaf(w, r[u].x, ag.x);
+          ag.y = fmaf(w, r[u].y, ag.y);
+          ag.z = fmaf(w, r[u].z, ag.z);
+          ag.w = fmaf(w, r[u].w, ag.w);
         }
       }
     }
