@@ -59,6 +59,54 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LayerNormArgs a) {
   }
 }
 
+// Fast layout (H = 128 P, phys column order): the row is read once as P float4 per lane and stays
+// in registers for the mean, the variance and the normalised store.
+template <int P>
+__global__ void __launch_bounds__(256) layernorm_fast_kernel(LayerNormArgs a) {
+  constexpr int H = 128 * P;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const float invH = 1.0f / (float)H;
+  float4 g[P], b[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    g[i] = reinterpret_cast<const float4 *>(a.gamma)[i * 32 + lane];
+    b[i] = reinterpret_cast<const float4 *>(a.beta)[i * 32 + lane];
+  }
+  for (uint64_t row = a.row_begin + warp; row < a.row_end; row += nwarps) {
+    bool iso = false;
+    if (a.row_ptr) iso = a.row_ptr[row] == a.row_ptr[row + 1];
+    const float4 *s4 = reinterpret_cast<const float4 *>(iso ? a.m + row * (uint64_t)a.ldm
+                                                            : a.d + row * (uint64_t)a.ldd);
+    float4 x[P];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      x[i] = s4[i * 32 + lane];
+      s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+    const float mean = warp_sum(s) * invH;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+      v = fmaf(x[i].x, x[i].x, fmaf(x[i].y, x[i].y, fmaf(x[i].z, x[i].z, fmaf(x[i].w, x[i].w, v))));
+    }
+    const float denom = sqrtf(warp_sum(v) * invH + a.eps);
+    float4 *d4 = reinterpret_cast<float4 *>(a.out + row * (uint64_t)H);
+#pragma unroll
+    for (int i = 0; i < P; ++i) {  // phys float4 index i*32+lane holds logical float4 lane*P+i
+      float4 o;
+      o.x = g[i].x * (x[i].x / denom) + b[i].x;
+      o.y = g[i].y * (x[i].y / denom) + b[i].y;
+      o.z = g[i].z * (x[i].z / denom) + b[i].z;
+      o.w = g[i].w * (x[i].w / denom) + b[i].w;
+      d4[lane * P + i] = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float *src, int64_t ld_src,
                                                         uint32_t row_floats, const uint32_t *idx,
                                                         uint64_t n_idx, float *dst) {
@@ -105,7 +153,17 @@ unsigned grid_for(uint64_t rows, int warps_per_block) {
 cudaError_t launch_layernorm(const LayerNormArgs &a, cudaStream_t s, uint64_t *launches) {
   if (a.row_end <= a.row_begin) return cudaSuccess;
   if (launches) ++*launches;
-  layernorm_kernel<<<grid_for(a.row_end - a.row_begin, 8), 256, 0, s>>>(a);
+  const unsigned grid = grid_for(a.row_end - a.row_begin, 8);
+  const bool al = ((a.ldd | a.ldm) & 3) == 0 && a.H == 128u * a.P;
+  switch (al ? (int)a.P : 0) {
+    case 1: layernorm_fast_kernel<1><<<grid, 256, 0, s>>>(a); break;
+    case 2: layernorm_fast_kernel<2><<<grid, 256, 0, s>>>(a); break;
+    case 3: layernorm_fast_kernel<3><<<grid, 256, 0, s>>>(a); break;
+    case 4: layernorm_fast_kernel<4><<<grid, 256, 0, s>>>(a); break;
+    case 6: layernorm_fast_kernel<6><<<grid, 256, 0, s>>>(a); break;
+    case 8: layernorm_fast_kernel<8><<<grid, 256, 0, s>>>(a); break;
+    default: layernorm_kernel<<<grid, 256, 0, s>>>(a);
+  }
   return cudaGetLastError();
 }
 
