@@ -413,7 +413,7 @@ __device__ __forceinline__ float reduce_scatter_xor(float (&v)[N]) {
 // Register budget: 16 resident warps per SM (128 registers).  Measured at 4M nodes: cutting it for 20 / 24
 // warps (96 / 80 registers, small spills) is slower (24.8 / 28.3 vs 23.8 ms), and so is requesting the
 // next step's rows one step ahead (167 registers, 12 warps: 26.6 ms).
-template <int HEADS, bool HALO>
+template <int HEADS, bool HALO, bool PREFETCH>
 __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args a, float scale_log2) {
   constexpr int H = 128, EB = 8, N = EB * HEADS, REP = 32 / N;
   // ONE warp per block: the node, its row bounds and every loop trip count then derive from
@@ -451,6 +451,16 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args 
       const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
       for (int jj = 0; jj < cnt; jj += EB) {
         float4 r[EB];  // slot u: edge jj + (u ^ my_slot)
+        if (PREFETCH && jj + EB < cnt) {
+          // one instruction pulls the NEXT step's 8 rows (32 lines of 128 B) towards L1: lane L takes
+          // line L % 4 of the row of edge jj + 8 + L / 4, so those loads find their data on chip
+          const int nsrc = jj + EB + my_slot;
+          const uint32_t ncol = __shfl_sync(0xffffffffu, my_col, nsrc < cnt ? nsrc : cnt - 1);
+          const float *nrow = (HALO && (uint64_t)ncol >= a.n_local)
+                                  ? a.halo + ((uint64_t)ncol - a.n_local) * H
+                                  : a.M + (uint64_t)ncol * a.ldm;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nrow + (lane & 3) * 32));
+        }
 #pragma unroll
         for (int u = 0; u < EB; ++u) {
           // slots beyond the row re-read its last edge (score masked below, weight 0)
@@ -534,10 +544,17 @@ cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, c
   if constexpr (HEADS <= 4) {
     if (batched) {
       uint64_t warps = rows < (uint64_t)sm_count * 64 ? rows : (uint64_t)sm_count * 64;
+      static int pf = -1;  // RUVGNN_R1_PF=0: no L1 prefetch of the next step's rows (A/B runs)
+      if (pf < 0) {
+        const char *e = getenv("RUVGNN_R1_PF");
+        pf = (e && atoi(e) == 0) ? 0 : 1;
+      }
       if (a.halo)
-        gather_r1_batched_kernel<HEADS, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+        gather_r1_batched_kernel<HEADS, true, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+      else if (pf)
+        gather_r1_batched_kernel<HEADS, false, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
       else
-        gather_r1_batched_kernel<HEADS, false><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+        gather_r1_batched_kernel<HEADS, false, false><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
       return cudaGetLastError();
     }
   }
