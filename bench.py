@@ -301,6 +301,7 @@ def main():
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
         exchange_ms = whole.exposed_wait_ms()
         del whole
+    exposed_wait_ms = part.exposed_wait_ms() if world > 1 else None  # of the last device-resident step
     ctx.set_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -386,7 +387,7 @@ def main():
                         "bytes_exchanged_rank0": int(part.bytes_exchanged), "exchange_ms_rank0": exchange_ms,
                         "plane": "all-gather" if part.dense else "all-to-all-v",
                         "interior_rows_rank0": int(part.interior_rows), "overlap": not a.no_overlap,
-                        "exposed_wait_ms_rank0": round(part.exposed_wait_ms(), 3)}
+                        "exposed_wait_ms_rank0": round(exposed_wait_ms, 3)}
     if not a.no_cpu_baseline and world == 1:
         cb, _, _ = cpu_baseline(a, layer, x, g, a.cpu_seconds)
         line["cpu_baseline"] = cb
