@@ -52,6 +52,60 @@ class CsrGraph:
         return DeviceGraph(ctx or default_context(0), self.row_ptr, self.col_idx, self.edge_w, n_cols, flags)
 
 
+def locality_order(g: CsrGraph) -> np.ndarray:
+    """A node order that pulls neighbours together (reverse Cuthill-McKee on the symmetrised
+    adjacency): ``perm[p]`` = the node that moves to position ``p``.
+
+    HNSW ids are insertion order, so a contiguous id range is a random node sample and nearly
+    every neighbour of a range partition is remote.  After this order most neighbours of a range
+    are inside it ("optional locality permutation applied identically to X, CSR rows
+    and col_idx; ... inverted on output").  Apply with :func:`permute_graph`, ``x[perm]`` and
+    ``out[inverse_permutation(perm)]``."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+    n = g.n_nodes
+    a = csr_matrix((np.ones(g.n_edges, dtype=np.int8), g.col_idx.astype(np.int64), g.row_ptr.astype(np.int64)),
+                   shape=(n, n))
+    return np.asarray(reverse_cuthill_mckee((a + a.T).tocsr(), symmetric_mode=True), dtype=np.int64)
+
+
+def inverse_permutation(perm: np.ndarray) -> np.ndarray:
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size, dtype=perm.dtype)
+    return inv
+
+
+def permute_graph(g: CsrGraph, perm: np.ndarray) -> CsrGraph:
+    """Relabels the nodes: new row ``p`` is old row ``perm[p]`` with every column ``j`` renamed to
+    ``inverse(perm)[j]``.  The order of the neighbours inside a row is kept, so every row goes
+    through exactly the arithmetic it had before (outputs are the old ones, permuted)."""
+    perm = np.asarray(perm, dtype=np.int64)
+    n = g.n_nodes
+    if perm.shape != (n,) or not np.array_equal(np.sort(perm), np.arange(n)):
+        raise InvalidInput("perm must be a permutation of the node ids")
+    inv = inverse_permutation(perm)
+    rp = g.row_ptr.astype(np.int64)
+    deg = np.diff(rp)[perm]
+    new_rp = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(deg, out=new_rp[1:].view(np.int64))
+    # edge e of new row p comes from old edge rp[perm[p]] + (e - new_rp[p])
+    src = np.repeat(rp[perm] - new_rp[:-1].astype(np.int64), deg) + np.arange(int(new_rp[-1]), dtype=np.int64)
+    return CsrGraph(new_rp, inv[g.col_idx[src].astype(np.int64)].astype(np.uint32), g.edge_w[src].copy())
+
+
+def remote_edge_fraction(g: CsrGraph, world: int) -> float:
+    """Share of the edges whose endpoint lies in another part of a ``world``-way contiguous range
+    partition (what the halo exchange has to serve)."""
+    n = g.n_nodes
+    if n == 0 or g.n_edges == 0:
+        return 0.0
+    bounds = np.array([(n * p) // world for p in range(world + 1)], dtype=np.int64)
+    owner_of_row = np.repeat(np.searchsorted(bounds, np.arange(n), side="right") - 1, g.degrees())
+    owner_of_col = np.searchsorted(bounds, g.col_idx.astype(np.int64), side="right") - 1
+    return float(np.mean(owner_of_row != owner_of_col))
+
+
 def pack_neighbour_lists(lists: Sequence[np.ndarray]) -> CsrGraph:
     """``lists[i]`` is node i's ``NEIGHBOUR_DTYPE`` record array (one HNSW level), in stored order."""
     lib = _lib.load()

@@ -385,3 +385,20 @@ def test_row_block_loop_changes_no_bit(tmp_path):
     for k in outs[0].files:
         assert np.isfinite(outs[0][k]).all()
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_locality_permutation_permutes_the_outputs_bit_exactly(ctx):
+    """graph.locality_order / permute_graph relabel nodes only: the device output of the permuted
+    problem is the original output, permuted, bit for bit (rows keep their neighbour order)."""
+    n, d, heads = 20000, 128, 4
+    layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=31), ctx=ctx,
+                             mode=rv.MODE_FP32_TC)
+    x = synth.make_features(n, d, seed=32)
+    g = synth.hnsw_like_graph(n, 8, seed=33, locality=0.7, window=200)
+    perm = rv.locality_order(g)
+    ref = layer.forward_graph(x, g.to_device(ctx))
+    got = layer.forward_graph(np.ascontiguousarray(x[perm]), rv.permute_graph(g, perm).to_device(ctx))
+    assert np.array_equal(got, ref[perm])
+    out = np.empty_like(got)
+    out[perm] = got  # == got[inverse_permutation(perm)]: back in the caller's node order
+    assert np.array_equal(out, ref) and np.array_equal(out, got[rv.inverse_permutation(perm)])

@@ -184,3 +184,31 @@ def test_product_package_never_touches_the_oracle():
     for p in (ROOT / "ruvector_b200").rglob("*"):
         if p.suffix in {".py", ".cu", ".cuh", ".cc", ".h"}:
             assert not pat.search(p.read_text()), p
+
+
+def test_locality_order_recovers_hidden_locality_and_keeps_every_row(built):
+    """Insertion-order ids hide the graph's locality: relabel a window graph at random, then let
+    locality_order() find an order in which range partitions keep their neighbours."""
+    from ruvector_b200.graph import inverse_permutation, locality_order, permute_graph, remote_edge_fraction
+
+    n = 20000
+    g = synth.hnsw_like_graph(n, 8, seed=21, locality=1.0, window=40, iso_frac=0.01)
+    rng = np.random.default_rng(3)
+    shuffle = rng.permutation(n)
+    hidden = permute_graph(g, shuffle)
+    assert remote_edge_fraction(g, 8) < 0.02 and remote_edge_fraction(hidden, 8) > 0.8
+    perm = locality_order(hidden)
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    found = permute_graph(hidden, perm)
+    assert remote_edge_fraction(found, 8) < 0.1
+    # rows are relabelled, never rewritten: row p of the permuted graph is row perm[p] with renamed columns
+    inv = inverse_permutation(perm)
+    for p in (0, 1, n // 2, n - 1):
+        s, t = int(found.row_ptr[p]), int(found.row_ptr[p + 1])
+        s0, t0 = int(hidden.row_ptr[perm[p]]), int(hidden.row_ptr[perm[p] + 1])
+        assert np.array_equal(found.col_idx[s:t], inv[hidden.col_idx[s0:t0]])
+        assert np.array_equal(found.edge_w[s:t], hidden.edge_w[s0:t0])
+    back = permute_graph(found, inv)
+    assert np.array_equal(back.row_ptr, hidden.row_ptr) and np.array_equal(back.col_idx, hidden.col_idx)
+    with pytest.raises(rv.GnnError):
+        permute_graph(g, np.zeros(n, dtype=np.int64))

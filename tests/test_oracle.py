@@ -215,3 +215,18 @@ def test_differentiable_search_top1(oracle):  # search.rs:206-225
     wts = np.empty(2, dtype=F32)
     k = oracle.lib.orc_differentiable_search(_p(q), _p(cands), 3, 3, 2, 1.0, idx.ctypes.data_as(C.POINTER(C.c_uint32)), _p(wts))
     assert k == 2 and idx[0] == 0 and idx[1] == 1 and wts[0] > wts[1]
+
+
+def test_node_relabelling_permutes_the_outputs_bit_exactly(oracle):
+    """A locality permutation (graph.permute_graph + x[perm]) changes no arithmetic: row p of the
+    permuted run equals row perm[p] of the original run, bit for bit."""
+    from ruvector_b200.graph import locality_order, permute_graph
+
+    n, d, heads = 600, 32, 4
+    layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=4))
+    x = synth.make_features(n, d, seed=5)
+    g = synth.hnsw_like_graph(n, 6, seed=6, iso_frac=0.03)
+    perm = locality_order(g)
+    ref = oracle.forward_graph(layer, x, g)
+    got = oracle.forward_graph(layer, np.ascontiguousarray(x[perm]), permute_graph(g, perm))
+    np.testing.assert_array_equal(got, ref[perm])
