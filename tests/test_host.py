@@ -212,3 +212,22 @@ def test_locality_order_recovers_hidden_locality_and_keeps_every_row(built):
     assert np.array_equal(back.row_ptr, hidden.row_ptr) and np.array_equal(back.col_idx, hidden.col_idx)
     with pytest.raises(rv.GnnError):
         permute_graph(g, np.zeros(n, dtype=np.int64))
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/ruvgnn.h is the drop-in boundary: it must compile as C99 (what cgo / bindgen / ctypes
+    generators read) and as C++, with no dependency beyond <stdint.h>/<stddef.h>."""
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "use.c"
+    src.write_text('#include "ruvgnn.h"\nint main(void) { ruvgnn_weights w; (void)w; return RUVGNN_OK; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", str(root / "include"), str(src)],
+                   check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", str(root / "include"), str(src)],
+                   check=True)
+    hpp = tmp_path / "use.cpp"
+    hpp.write_text('#include "ruvgnn.hpp"\nint main() { return 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", str(root / "include"), str(hpp)],
+                   check=True)
