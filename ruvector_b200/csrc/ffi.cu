@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "layer_host.h"
+#include "abi_guard.h"
 
 namespace ruvgnn {
 
@@ -620,6 +621,7 @@ const char *ruvgnn_last_error(void) { return g_last_error.c_str(); }
 uint32_t ruvgnn_abi_version(void) { return 1; }
 
 int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
+  RUVGNN_ABI_TRY
   if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
   *out = nullptr;
   int ndev = 0;
@@ -658,6 +660,7 @@ int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
   RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   *out = c.release();
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
@@ -688,27 +691,34 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
 }
 
 int32_t ruvgnn_sync(ruvgnn_ctx *c) {
+  RUVGNN_ABI_TRY
   if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
   RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 void *ruvgnn_ctx_stream(ruvgnn_ctx *c) { return c ? c->stream : nullptr; }
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
 
 int32_t ruvgnn_ctx_set_sm_limit(ruvgnn_ctx *c, int32_t sms) {
+  RUVGNN_ABI_TRY
   if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
   if (sms < 0) sms = c->sm_count_dev + sms > 1 ? c->sm_count_dev + sms : 1;  // reserve |sms|
   c->sm_count = (sms == 0 || sms > c->sm_count_dev) ? c->sm_count_dev : sms;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_ctx_set_timing(ruvgnn_ctx *c, int32_t on) {
+  RUVGNN_ABI_TRY
   if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
   c->timing_on = on != 0;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms6) {
+  RUVGNN_ABI_TRY
   if (!c || !ms6) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (c->ring_count == 0) return fail(RUVGNN_ERR_INVALID_INPUT, "no timed forward since last query");
   RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -737,16 +747,20 @@ int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms6) {
   for (int i = 0; i < 6; ++i) ms6[i] = (float)(acc[i] / nslots);
   c->ring_count = 0;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_validate(uint32_t input_dim, uint32_t hidden_dim, uint32_t heads,
                               float dropout) {
+  RUVGNN_ABI_TRY
   return check_config(input_dim, hidden_dim, heads, dropout);
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_create(ruvgnn_ctx *ctx, uint32_t input_dim, uint32_t hidden_dim,
                             uint32_t heads, float dropout, const ruvgnn_weights *w,
                             ruvgnn_layer **out) {
+  RUVGNN_ABI_TRY
   if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
   *out = nullptr;
   int32_t rc = check_config(input_dim, hidden_dim, heads, dropout);
@@ -772,9 +786,11 @@ int32_t ruvgnn_layer_create(ruvgnn_ctx *ctx, uint32_t input_dim, uint32_t hidden
   h.gamma.assign(w->gamma, w->gamma + hidden_dim);
   h.beta.assign(w->beta, w->beta + hidden_dim);
   return make_layer(ctx, std::move(L), out);
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_from_json(ruvgnn_ctx *ctx, const char *json, size_t len, ruvgnn_layer **out) {
+  RUVGNN_ABI_TRY
   if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
   *out = nullptr;
   if (!ctx || !json) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx / json is null");
@@ -782,9 +798,11 @@ int32_t ruvgnn_layer_from_json(ruvgnn_ctx *ctx, const char *json, size_t len, ru
   std::string err = parse_layer_json(json, len, L->host);
   if (!err.empty()) return fail(RUVGNN_ERR_INVALID_INPUT, err);
   return make_layer(ctx, std::move(L), out);
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_to_json(const ruvgnn_layer *layer, char *buf, size_t cap, size_t *needed) {
+  RUVGNN_ABI_TRY
   if (!layer) return fail(RUVGNN_ERR_INVALID_INPUT, "layer is null");
   const std::string s = emit_layer_json(layer->host);
   if (needed) *needed = s.size();
@@ -794,10 +812,12 @@ int32_t ruvgnn_layer_to_json(const ruvgnn_layer *layer, char *buf, size_t cap, s
     buf[n] = 0;
   }
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_json_normalize(const char *json, size_t len, char *buf, size_t cap,
                                     size_t *needed) {
+  RUVGNN_ABI_TRY
   if (!json) return fail(RUVGNN_ERR_INVALID_INPUT, "json is null");
   LayerHost h;
   std::string err = parse_layer_json(json, len, h);
@@ -812,19 +832,23 @@ int32_t ruvgnn_layer_json_normalize(const char *json, size_t len, char *buf, siz
     buf[n] = 0;
   }
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_dims(const ruvgnn_layer *layer, uint32_t *input_dim, uint32_t *hidden_dim,
                           uint32_t *heads, float *dropout) {
+  RUVGNN_ABI_TRY
   if (!layer) return fail(RUVGNN_ERR_INVALID_INPUT, "layer is null");
   if (input_dim) *input_dim = layer->D;
   if (hidden_dim) *hidden_dim = layer->H;
   if (heads) *heads = layer->heads;
   if (dropout) *dropout = layer->host.dropout;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode) {
+  RUVGNN_ABI_TRY
   if (!layer) return fail(RUVGNN_ERR_INVALID_INPUT, "layer is null");
   if (mode > RUVGNN_MODE_TF32) return fail(RUVGNN_ERR_INVALID_INPUT, "unknown mode");
   if (mode != RUVGNN_MODE_FP32_SIMT && !layer->tc.usable)
@@ -832,6 +856,7 @@ int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode) {
                 "tensor-core modes need input_dim % 32 == 0 and hidden_dim % 64 == 0");
   layer->mode = mode;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 void ruvgnn_layer_destroy(ruvgnn_layer *L) {
@@ -845,6 +870,7 @@ void ruvgnn_layer_destroy(ruvgnn_layer *L) {
 int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
                             const uint64_t *row_ptr, const uint32_t *col_idx, const float *edge_w,
                             uint32_t flags, ruvgnn_graph **out) {
+  RUVGNN_ABI_TRY
   if (!out) return fail(RUVGNN_ERR_INVALID_INPUT, "out is null");
   *out = nullptr;
   if (!ctx || !row_ptr) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx / row_ptr is null");
@@ -903,19 +929,23 @@ int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
   }
   *out = g.release();
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_graph_dims(const ruvgnn_graph *g, uint64_t *n_nodes, uint64_t *n_cols,
                           uint64_t *n_edges) {
+  RUVGNN_ABI_TRY
   if (!g) return fail(RUVGNN_ERR_INVALID_INPUT, "graph is null");
   if (n_nodes) *n_nodes = g->n_nodes;
   if (n_cols) *n_cols = g->n_cols;
   if (n_edges) *n_edges = g->n_edges;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_graph_download(const ruvgnn_graph *g, uint64_t *row_ptr, uint32_t *col_idx,
                               float *edge_w) {
+  RUVGNN_ABI_TRY
   if (!g) return fail(RUVGNN_ERR_INVALID_INPUT, "graph is null");
   DeviceGuard dg(g->device);
   if (row_ptr)
@@ -928,6 +958,7 @@ int32_t ruvgnn_graph_download(const ruvgnn_graph *g, uint64_t *row_ptr, uint32_t
     RUVGNN_CUDA_TRY(
         cudaMemcpy(edge_w, g->edge_w, g->n_edges * sizeof(float), cudaMemcpyDeviceToHost));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 void ruvgnn_graph_destroy(ruvgnn_graph *g) {
@@ -941,6 +972,7 @@ void ruvgnn_graph_destroy(ruvgnn_graph *g) {
 
 int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
                              const float *x, float *out, uint32_t flags) {
+  RUVGNN_ABI_TRY
   if (!c || !L || !G || !x || !out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (L->device != c->device || G->device != c->device)
     return fail(RUVGNN_ERR_INVALID_INPUT, "layer / graph live on another device than ctx");
@@ -1029,11 +1061,13 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   }
   if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
                              const ruvgnn_graph *const *graphs, uint32_t n_layers, const float *x,
                              float *out, uint32_t flags) {
+  RUVGNN_ABI_TRY
   if (!c || !layers || !graphs || !x || !out || n_layers == 0)
     return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   const uint64_t n = graphs[0] ? graphs[0]->n_nodes : 0;
@@ -1094,11 +1128,13 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
                                     cudaMemcpyDeviceToHost, c->stream));
   if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_forward_node(ruvgnn_ctx *c, const ruvgnn_layer *L, const float *x,
                                   uint32_t x_len, const float *nbrs, uint32_t k, const float *w,
                                   uint32_t n_w, float *out) {
+  RUVGNN_ABI_TRY
   if (!c || !L || !x || !out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (x_len != L->D) {
     char buf[96];
@@ -1135,10 +1171,12 @@ int32_t ruvgnn_layer_forward_node(ruvgnn_ctx *c, const ruvgnn_layer *L, const fl
   if (rc) return rc;
   memcpy(out, O.data(), sizeof(float) * H);
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_local,
                              const float *x_dev) {
+  RUVGNN_ABI_TRY
   if (!c || !L || !x_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
@@ -1151,10 +1189,12 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   int32_t rc = do_project(c, L, n_local, x_dev);
   if (c->timing_on) cudaEventRecord(c->ev[2], c->stream);
   return rc;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_local,
                                   const float *x_dev, uint64_t row_begin, uint64_t row_end) {
+  RUVGNN_ABI_TRY
   if (!c || !L || !x_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (row_end > n_local || row_begin > row_end)
     return fail(RUVGNN_ERR_INVALID_INPUT, "row range out of bounds");
@@ -1169,6 +1209,7 @@ int32_t ruvgnn_layer_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t
   int32_t rc = do_project_rows(c, L, n_local, x_dev, row_begin, row_end);
   if (c->timing_on) cudaEventRecord(c->ev[2], c->stream);
   return rc;
+  RUVGNN_ABI_CATCH
 }
 
 uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *L) {
@@ -1178,6 +1219,7 @@ uint32_t ruvgnn_layer_halo_width(const ruvgnn_layer *L) {
 
 int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *idx_dev,
                          uint64_t n_idx, float *send_dev) {
+  RUVGNN_ABI_TRY
   if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_idx == 0) return RUVGNN_OK;
   if (!idx_dev || !send_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
@@ -1188,10 +1230,12 @@ int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *i
   RUVGNN_CUDA_TRY(launch_pack_rows(w.halo_src, w.ldm, w.halo_w, idx_dev, n_idx, send_dev,
                                    c->stream, &c->launches));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_messages(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t row_begin,
                               uint64_t n_rows, float *out_dev) {
+  RUVGNN_ABI_TRY
   if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_rows == 0) return RUVGNN_OK;
   if (!out_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
@@ -1207,10 +1251,12 @@ int32_t ruvgnn_layer_messages(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t row
                                     (size_t)w.ldm * sizeof(float), rowb, n_rows,
                                     cudaMemcpyDeviceToDevice, c->stream));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_expand_halo(ruvgnn_ctx *c, const ruvgnn_layer *L, const float *m_rows,
                                  uint64_t n_rows, float *halo_dev) {
+  RUVGNN_ABI_TRY
   if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_rows == 0) return RUVGNN_OK;
   if (!m_rows || !halo_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
@@ -1238,11 +1284,13 @@ int32_t ruvgnn_layer_expand_halo(ruvgnn_ctx *c, const ruvgnn_layer *L, const flo
   RUVGNN_CUDA_TRY(cudaMemcpy2DAsync(halo_dev + 2 * H, 3 * rowb, m_rows, rowb, rowb, n_rows,
                                     cudaMemcpyDeviceToDevice, c->stream));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
                                       const float *halo_dev, uint64_t row_begin, uint64_t row_end,
                                       float *out_dev) {
+  RUVGNN_ABI_TRY
   if (!c || !L || !G || !out_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (c->proj_rows != G->n_nodes || c->proj_H != L->H)
     return fail(RUVGNN_ERR_INVALID_INPUT,
@@ -1260,6 +1308,7 @@ int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, cons
     cudaEventRecord(c->ev[5], c->stream);
   }
   return rc;
+  RUVGNN_ABI_CATCH
 }
 
 }  // extern "C"
@@ -1314,6 +1363,7 @@ extern "C" int32_t ruvgnn_differentiable_search(ruvgnn_ctx *c, const float *quer
                                                 uint64_t n_cand, uint32_t dim, uint32_t k,
                                                 float temperature, uint32_t *idx_out, float *w_out,
                                                 uint32_t *k_out, uint32_t flags) {
+  RUVGNN_ABI_TRY
   if (!c || !k_out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   *k_out = 0;
   if (n_cand == 0 || n_queries == 0) return RUVGNN_OK;  // search.rs:62-64: empty result
@@ -1348,6 +1398,7 @@ extern "C" int32_t ruvgnn_differentiable_search(ruvgnn_ctx *c, const float *quer
   RUVGNN_CUDA_TRY(cudaMemcpy(w_out, wd.p, n_queries * ke * sizeof(float), kind));
   *k_out = ke;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queries,
@@ -1358,6 +1409,7 @@ extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queri
                                                const ruvgnn_layer *const *layers,
                                                uint32_t n_levels, float *out,
                                                uint32_t out_capacity_floats, uint32_t *out_dim) {
+  RUVGNN_ABI_TRY
   if (!c || !queries || !out || !out_dim) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_levels && (!level_emb || !level_rows || !level_dim || !layers))
     return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
@@ -1437,4 +1489,5 @@ extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queri
                                   c->stream));
   RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }

@@ -18,10 +18,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/ruvgnn.h"
+#include "abi_guard.h"
 
 namespace ruvgnn {
 int32_t fail(int32_t code, const std::string &msg);
@@ -76,6 +78,7 @@ struct ruvgnn_hnsw_dump {
 extern "C" {
 
 int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out) {
+  RUVGNN_ABI_TRY
   if (!graph_path || !out) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   *out = nullptr;
   FILE *f = fopen(graph_path, "rb");
@@ -90,11 +93,9 @@ int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out) {
   }
   fclose(f);
   Reader r{buf.data(), buf.data() + buf.size()};
-  ruvgnn_hnsw_dump *d = new ruvgnn_hnsw_dump();
-  auto bad = [&](const std::string &m) {
-    delete d;
-    return fail(RUVGNN_ERR_INVALID_INPUT, "hnsw dump: " + m);
-  };
+  std::unique_ptr<ruvgnn_hnsw_dump> owner(new ruvgnn_hnsw_dump());
+  ruvgnn_hnsw_dump *d = owner.get();
+  auto bad = [&](const std::string &m) { return fail(RUVGNN_ERR_INVALID_INPUT, "hnsw dump: " + m); };
   const uint32_t magic = r.get<uint32_t>();
   if (magic == MAGICDESCR_2) d->format_version = 2;
   else if (magic == MAGICDESCR_3) d->format_version = 3;
@@ -130,6 +131,9 @@ int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out) {
     for (uint64_t j = 0; j < npts; ++j) {
       if (r.get<uint32_t>() != MAGICPOINT || !r.ok) return bad("bad magic at point beginning");
       const uint64_t origin = r.get<uint64_t>();
+      // rows are addressed by origin_id and columns are u32: anything larger cannot be a node
+      // (and origin + 1 below must not wrap)
+      if (!r.ok || origin >= 0xffffffffull) return bad("origin_id exceeds the u32 node index range");
       uint8_t layer = (uint8_t)b;
       if (full) {
         layer = r.get<uint8_t>();
@@ -155,8 +159,9 @@ int32_t ruvgnn_hnsw_dump_open(const char *graph_path, ruvgnn_hnsw_dump **out) {
   d->entry_point = r.get<uint64_t>();
   if (!r.ok) return bad("truncated before the entry point");
   if (d->origin.size() != d->nb_point) return bad("point count differs from the description");
-  *out = d;
+  *out = owner.release();
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 void ruvgnn_hnsw_dump_close(ruvgnn_hnsw_dump *d) { delete d; }
@@ -164,6 +169,7 @@ void ruvgnn_hnsw_dump_close(ruvgnn_hnsw_dump *d) { delete d; }
 int32_t ruvgnn_hnsw_dump_info(const ruvgnn_hnsw_dump *d, uint64_t *nb_point, uint64_t *n_ids,
                               uint32_t *nb_layer, uint32_t *max_nb_connection, uint64_t *dimension,
                               uint32_t *dumpmode, uint64_t *entry_point) {
+  RUVGNN_ABI_TRY
   if (!d) return fail(RUVGNN_ERR_INVALID_INPUT, "dump is null");
   if (nb_point) *nb_point = d->nb_point;
   if (n_ids) *n_ids = d->n_ids;
@@ -173,17 +179,21 @@ int32_t ruvgnn_hnsw_dump_info(const ruvgnn_hnsw_dump *d, uint64_t *nb_point, uin
   if (dumpmode) *dumpmode = d->dumpmode;
   if (entry_point) *entry_point = d->entry_point;
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_hnsw_dump_level_edges(const ruvgnn_hnsw_dump *d, uint32_t level, uint64_t *n_edges) {
+  RUVGNN_ABI_TRY
   if (!d || !n_edges) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (level >= d->nb_layer) return fail(RUVGNN_ERR_INVALID_INPUT, "level out of range");
   *n_edges = d->level_edges[level];
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 int32_t ruvgnn_hnsw_dump_level_csr(const ruvgnn_hnsw_dump *d, uint32_t level, uint64_t n_nodes,
                                    uint64_t *row_ptr, uint32_t *col_idx, float *edge_w) {
+  RUVGNN_ABI_TRY
   if (!d || !row_ptr) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (level >= d->nb_layer) return fail(RUVGNN_ERR_INVALID_INPUT, "level out of range");
   if (n_nodes < d->n_ids)
@@ -212,6 +222,7 @@ int32_t ruvgnn_hnsw_dump_level_csr(const ruvgnn_hnsw_dump *d, uint32_t level, ui
     }
   }
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/ruvgnn.h"
+#include "abi_guard.h"
 
 namespace ruvgnn {
 int32_t fail(int32_t code, const std::string &msg);
@@ -21,6 +22,7 @@ extern "C" int32_t ruvgnn_pack_neighbours(uint64_t n_nodes, const void *const *l
                                           const uint64_t *counts, size_t stride, size_t id_offset,
                                           size_t dist_offset, uint64_t *row_ptr, uint32_t *col_idx,
                                           float *edge_w) {
+  RUVGNN_ABI_TRY
   if (!counts || !row_ptr || (n_nodes && !lists))
     return ruvgnn::fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (stride < sizeof(uint64_t) + sizeof(float) || id_offset + sizeof(uint64_t) > stride ||
@@ -51,4 +53,5 @@ extern "C" int32_t ruvgnn_pack_neighbours(uint64_t n_nodes, const void *const *l
     row_ptr[i + 1] = e;
   }
   return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
 }

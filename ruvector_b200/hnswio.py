@@ -39,9 +39,14 @@ class HnswDump:
     def level_csr(self, level: int = 0, n_nodes: int | None = None) -> CsrGraph:
         n = self.n_ids if n_nodes is None else n_nodes
         e = self.level_edges(level)
-        rp = np.empty(n + 1, dtype=np.uint64)
-        ci = np.empty(e, dtype=np.uint32)
-        ew = np.empty(e, dtype=np.float32)
+        try:
+            rp = np.empty(n + 1, dtype=np.uint64)
+            ci = np.empty(e, dtype=np.uint32)
+            ew = np.empty(e, dtype=np.float32)
+        except (MemoryError, ValueError) as err:  # e.g. one stray origin_id of 2^31 in a small dump
+            from .errors import InvalidInput
+
+            raise InvalidInput(f"Invalid input: cannot hold a CSR of {n} rows / {e} edges: {err}") from None
         _lib.check(self._lib.ruvgnn_hnsw_dump_level_csr(
             self.handle, level, n, rp.ctypes.data_as(C.POINTER(C.c_uint64)),
             ci.ctypes.data_as(C.POINTER(C.c_uint32)), ew.ctypes.data_as(_lib.c_float_p)))

@@ -92,3 +92,35 @@ def test_corrupt_dumps_are_rejected(tmp_path, built):
     write_graph_dump(empty, [])
     d = HnswDump(empty)
     assert d.nb_point == 0 and d.level_csr(0).n_nodes == 0
+
+
+def test_mutated_files_never_crash_the_native_parsers(tmp_path, built):
+    """600 mutations (truncate / flip / extreme 8-byte fields / duplicate / delete slices) of a valid
+    dump and of a layer JSON: each must parse or be rejected with a GnnError status.  Runs in a child
+    process (scripts/fuzz_parsers.py) so that a crash is an exit code, not a dead test session."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    res = subprocess.run([sys.executable, str(root / "scripts" / "fuzz_parsers.py"), str(tmp_path), "300"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "FUZZ OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+
+
+def test_absurd_origin_id_is_rejected_at_open(tmp_path, built):
+    import struct
+
+    pts, _ = make_points(30, 4, seed=7)
+    path = tmp_path / "ok.hnsw.graph"
+    write_graph_dump(path, pts)
+    raw = bytearray(path.read_bytes())
+    hdr = 4 + 1 + 1 + 8 + 1 + 8 * 3 + 8 + len("DistCosine") + 8 + len("f32")
+    pos = hdr + 1 + 4 + 8 + 4  # nb_layer, MAGICLAYER, nb_point, MAGICPOINT -> origin_id of the first point
+    for value in (2**64 - 1, 2**32 - 1, 2**40):
+        raw[pos:pos + 8] = struct.pack("=Q", value)
+        bad = tmp_path / "bad.hnsw.graph"
+        bad.write_bytes(bytes(raw))
+        with pytest.raises(rv.InvalidInput) as e:
+            HnswDump(bad)
+        assert "origin_id exceeds" in str(e.value)
