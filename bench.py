@@ -371,6 +371,29 @@ def main():
         except (ValueError, OSError):
             pass
 
+    # Second roofline: the six projection GEMMs against the tensor pipe.  USEFUL FLOPs per node
+    # = 2 (D H + 11 H^2); the FP32-parity path issues three TF32 MMAs per product (3xTF32), so the pipe does
+    # 3x that.  Peak = half the measured dense bf16 rate (TF32 runs at half the bf16 rate).  The time is the
+    # K-proj + K-upd stage time of the last step; K-upd includes the LayerNorm kernel (~1% of the layer).
+    gemm_ms = float(stage[0] + stage[2])
+    D = a.dim
+    flops_useful = 2.0 * (D * H + 11.0 * H * H) * n
+    passes = 3 if mode == _lib.MODE_FP32_TC else 1
+    tf32_peak, tf32_src = None, None
+    try:
+        mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        tf32_peak, tf32_src = float(mp["bf16_tflops"]) / 2.0, "measured bf16_tflops (burst) / 2"
+    except (OSError, ValueError, KeyError):
+        tf32_peak, tf32_src = 1125.0, "nominal 2.25 PFLOP/s bf16 / 2"
+    if gemm_ms > 0 and mode != _lib.MODE_FP32_SIMT:
+        useful = flops_useful / (gemm_ms * 1e-3) / 1e12
+        roof_gemm = {"kernels": "gemm_tc_kernel / gemm_tc_ts_kernel (K-proj + K-upd, 6 GEMMs)", "bound": "tensor",
+                     "achieved": useful * passes, "achieved_useful": useful, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": useful * passes / tf32_peak, "frac_useful": useful / tf32_peak,
+                     "mma_passes_per_product": passes, "peak_source": tf32_src, "ms": gemm_ms}
+    else:
+        roof_gemm = None
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -381,6 +404,7 @@ def main():
                    "parallelism": f"range-partition x{n_gpus}" if n_gpus > 1 else "single"},
         "edges_per_sec": E_total / (ms_per_step * 1e-3),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+        "roofline_projections": roof_gemm,
     }
     if world > 1:
         line["halo"] = {"rows_received_rank0": part.plan.n_halo, "rows_sent_rank0": int(part.plan.send_idx.size),
