@@ -17,12 +17,12 @@ import numpy as np
 F = np.float32
 
 
-def linear(w, b, x):
+def linear(w, b, x, F=F):
     """layer.rs:37-41 -- y = W x + b for a batch of rows x[N, in]; w is [out, in]."""
     return (x.astype(F) @ w.astype(F).T + b.astype(F)).astype(F)
 
 
-def layer_norm(gamma, beta, eps, x):
+def layer_norm(gamma, beta, eps, x, F=F):
     """layer.rs:68-81 -- biased variance, (x-mean)/sqrt(var+eps)*gamma+beta."""
     x = x.astype(F)
     mean = x.mean(axis=-1, keepdims=True, dtype=F)
@@ -30,19 +30,33 @@ def layer_norm(gamma, beta, eps, x):
     return ((x - mean) / np.sqrt(var + F(eps)) * gamma + beta).astype(F)
 
 
-def sigmoid(x):
+def sigmoid(x, F=F):
     """layer.rs:278-285 -- the two branches are the same function."""
     x = x.astype(F)
     pos = F(1) / (F(1) + np.exp(-np.abs(x)))
     return np.where(x > 0, pos, F(1) - pos).astype(F)
 
 
-def forward_graph(weights: dict, input_dim, hidden_dim, heads, dropout, x, row_ptr, col_idx, edge_w):
+def forward_graph(weights: dict, input_dim, hidden_dim, heads, dropout, x, row_ptr, col_idx, edge_w, dtype=np.float32):
     """out[i] = RuvectorLayer.forward(x[i], x[N(i)], w[i]) for every node (Jacobi).
 
     ``weights`` maps the 12 linear names to (W[out,in], b[out]) plus
     ``gamma``, ``beta``, ``eps`` -- the serde field names of layer.rs:315-333.
+    ``dtype=np.float64`` evaluates the same formulas in double precision: the yardstick for how
+    much of the 1e-4 tolerance the float32 arithmetic of the reference itself uses up.
     """
+    F = np.dtype(dtype).type
+
+    def linear(w, b, x_):
+        return globals()["linear"](w, b, x_, F)
+
+    def sigmoid(x_):
+        return globals()["sigmoid"](x_, F)
+
+    def layer_norm(g_, b_, e_, x_):
+        return globals()["layer_norm"](np.asarray(g_, dtype=F), np.asarray(b_, dtype=F), e_, x_, F)
+
+    x = np.asarray(x, dtype=F)
     n = x.shape[0]
     H, h = hidden_dim, heads
     dh = H // h

@@ -230,3 +230,19 @@ def test_node_relabelling_permutes_the_outputs_bit_exactly(oracle):
     ref = oracle.forward_graph(layer, x, g)
     got = oracle.forward_graph(layer, np.ascontiguousarray(x[perm]), permute_graph(g, perm))
     np.testing.assert_array_equal(got, ref[perm])
+
+
+def test_float32_oracle_sits_two_orders_below_the_tolerance(oracle):
+    """The same formulas in float64 (NumPy twin, dtype=float64) vs the float32 C oracle: the rounding
+    noise of the reference's own arithmetic is ~1e-6 row-relative, so the 1e-4 parity bound is not
+    consumed by the yardstick itself."""
+    n, d, heads, m = 400, 128, 4, 16
+    w = synth.make_weights(d, d, seed=41)
+    layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=w)
+    x = synth.make_features(n, d, seed=42)
+    g = synth.hnsw_like_graph(n, m, seed=43, iso_frac=0.02)
+    c_out = oracle.forward_graph(layer, x, g)
+    exact = oracle_np.forward_graph(w, d, d, heads, 0.1, x, g.row_ptr, g.col_idx, g.edge_w, dtype=np.float64)
+    assert exact.dtype == np.float64
+    err = rel_rows(c_out.astype(np.float64), exact)
+    assert err.max() < 5e-6 and np.abs(c_out - exact).max() < 2e-5
