@@ -30,3 +30,26 @@ def test_cpp_forward_tests(built, tmp_path):
     res = subprocess.run([str(build_exe(tmp_path)), "all"], capture_output=True, text=True, timeout=300)
     print(res.stdout, res.stderr)
     assert res.returncode == 0 and res.stdout.strip().endswith("OK")
+
+
+def build_c_exe(tmp_path):
+    exe = tmp_path / "test_abi"
+    lib = _lib.lib_path()
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"),
+                    str(ROOT / "tests" / "c" / "test_abi.c"), "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}", "-lm"],
+                   check=True)
+    return exe
+
+
+def test_plain_c_caller_of_the_abi(built, tmp_path):
+    """tests/c/test_abi.c: the boundary as a cgo / Rust FFI / JNI binding sees it (C99, no C++)."""
+    res = subprocess.run([str(build_c_exe(tmp_path))], capture_output=True, text=True, timeout=120)
+    print(res.stdout, res.stderr)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK")
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_forward(built, tmp_path):
+    res = subprocess.run([str(build_c_exe(tmp_path)), "gpu"], capture_output=True, text=True, timeout=300)
+    print(res.stdout, res.stderr)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK")
