@@ -355,7 +355,7 @@ def main():
     agg_ms = float(stage[1]) if stage[1] > 0 else None
     R = int(_lib.load().ruvgnn_layer_halo_width(layer._device_layer())) // H
     bytes_launch = agg_bytes_per_node(H, E, n, R, a.heads) * n
-    roof = {"kernel": f"{'gather_r1_kernel' if R == 1 else 'gather_fast_kernel'} (K-agg, R={R})", "bound": "hbm",
+    roof = {"kernel": f"{'gather_r1_batched_kernel' if R == 1 else 'gather_fast_kernel'} (K-agg, R={R})", "bound": "hbm",
             "achieved": (bytes_launch / (agg_ms * 1e-3) / 1e9) if agg_ms else None, "peak": peak, "unit": "GB/s",
             "frac": (bytes_launch / (agg_ms * 1e-3) / 1e9 / peak) if agg_ms else None,
             "traffic": None, "peak_source": peak_src,
