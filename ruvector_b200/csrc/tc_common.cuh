@@ -153,15 +153,46 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
          ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// Gate activations of the tensor-core path.  The epilogue warps run them on 128 x BN outputs per
+// tile (one warp per scheduler), and with libm expf / tanhf and IEEE divides (~45 instructions per
+// element, dependent chains) that is what bounds the short-K shapes (H = 128: the gates epilogue of
+// a tile outlasts its 8-k-block main loop).  MUFU forms: exp2 (ex2.approx, 2^-22 relative) and
+// reciprocal (rcp.approx, 1 ulp) -- ~7 instructions per sigmoid, ~9 per tanh, absolute error
+// < 5e-7, two orders below the 1e-4 parity bound.  -DRUVGNN_PRECISE_ACT restores libm; the FP32
+// SIMT mode (gemm_simt.cu) always uses libm.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float sigmoid_ref(float x) {
   // GRUCell::sigmoid (layer.rs:278-285): x > 0 ? 1/(1+exp(-x)) : exp(x)/(1+exp(x)).  Both
-  // branches use exp(-|x|); written branch-free with one exp and one divide (the x <= 0 case
-  // multiplies by the reciprocal instead of dividing: <= 1 ulp).
+  // branches use exp(-|x|); written branch-free with one exp and one reciprocal.
+#ifdef RUVGNN_PRECISE_ACT
   const float t = expf(-fabsf(x));
   const float r = 1.0f / (1.0f + t);
+#else
+  const float t = ex2_fast(-1.4426950408889634f * fabsf(x));
+  const float r = rcp_fast(1.0f + t);
+#endif
   return x > 0.f ? r : t * r;
 }
 
+__device__ __forceinline__ float tanh_ref(float x) {
+  // GRUCell candidate state (layer.rs:268-270): tanh(x) = sign(x) (1 - e) / (1 + e), e = exp(-2|x|)
+#ifdef RUVGNN_PRECISE_ACT
+  return tanhf(x);
+#else
+  const float e = ex2_fast(-2.8853900817779268f * fabsf(x));
+  return copysignf((1.0f - e) * rcp_fast(1.0f + e), x);
+#endif
+}
 
 // Fused epilogue of one 32-row x 32-column accumulator chunk owned by one warp.
 // tcgen05.ld hands every lane one ROW (32 consecutive columns in registers); touching global
@@ -226,10 +257,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, int64_t row0, 
     } else {  // EPI_GRU (layer.rs:266-274, 448-451)
       const float4 z = x1[p], m = x2[p];
       float4 o;
-      o.x = ((1.0f - z.x) * m.x + z.x * tanhf(a.x)) * g.keep;
-      o.y = ((1.0f - z.y) * m.y + z.y * tanhf(a.y)) * g.keep;
-      o.z = ((1.0f - z.z) * m.z + z.z * tanhf(a.z)) * g.keep;
-      o.w = ((1.0f - z.w) * m.w + z.w * tanhf(a.w)) * g.keep;
+      o.x = ((1.0f - z.x) * m.x + z.x * tanh_ref(a.x)) * g.keep;
+      o.y = ((1.0f - z.y) * m.y + z.y * tanh_ref(a.y)) * g.keep;
+      o.z = ((1.0f - z.z) * m.z + z.z * tanh_ref(a.z)) * g.keep;
+      o.w = ((1.0f - z.w) * m.w + z.w * tanh_ref(a.w)) * g.keep;
       *reinterpret_cast<float4 *>(g.out + (row0 + r) * g.ldo + c) = o;
     }
   }
@@ -290,10 +321,10 @@ __device__ __forceinline__ void epilogue_chunk_rowwise(const GemmArgs &g, int64_
       for (int j = 0; j < 8; ++j) {
         const float4 z = z4[j], m = m4[j];
         float4 r;
-        r.x = ((1.0f - z.x) * m.x + z.x * tanhf(v[4 * j + 0])) * g.keep;
-        r.y = ((1.0f - z.y) * m.y + z.y * tanhf(v[4 * j + 1])) * g.keep;
-        r.z = ((1.0f - z.z) * m.z + z.z * tanhf(v[4 * j + 2])) * g.keep;
-        r.w = ((1.0f - z.w) * m.w + z.w * tanhf(v[4 * j + 3])) * g.keep;
+        r.x = ((1.0f - z.x) * m.x + z.x * tanh_ref(v[4 * j + 0])) * g.keep;
+        r.y = ((1.0f - z.y) * m.y + z.y * tanh_ref(v[4 * j + 1])) * g.keep;
+        r.z = ((1.0f - z.z) * m.z + z.z * tanh_ref(v[4 * j + 2])) * g.keep;
+        r.w = ((1.0f - z.w) * m.w + z.w * tanh_ref(v[4 * j + 3])) * g.keep;
         o[j] = r;
       }
     }
