@@ -90,7 +90,9 @@ typedef struct {
 } ruvgnn_weights;
 
 /* Arithmetic mode of the dense projections.  The gather/aggregate kernel is
- * always FP32. */
+ * always FP32.  A new layer starts in RUVGNN_MODE_FP32_TC when its shape allows it
+ * (input_dim % 32 == 0 and hidden_dim % 32 == 0), else in RUVGNN_MODE_FP32_SIMT; there is no
+ * silent switch afterwards: ruvgnn_layer_set_mode on an unsupported shape fails. */
 #define RUVGNN_MODE_FP32_SIMT 0 /* FP32 FFMA GEMMs (any shape; the parity reference on device) */
 #define RUVGNN_MODE_FP32_TC 1   /* tcgen05 3xTF32 error-compensated, FP32 accumulate: FP32-grade */
 #define RUVGNN_MODE_TF32 2      /* tcgen05 single-pass TF32: NOT parity, own tolerance */
@@ -118,6 +120,7 @@ int32_t ruvgnn_layer_json_normalize(const char *json, size_t len, char *buf, siz
 int32_t ruvgnn_layer_dims(const ruvgnn_layer *layer, uint32_t *input_dim, uint32_t *hidden_dim,
                           uint32_t *heads, float *dropout);
 int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode);
+uint32_t ruvgnn_layer_mode(const ruvgnn_layer *layer);
 void ruvgnn_layer_destroy(ruvgnn_layer *layer);
 
 /* ---- graph: HNSW neighbour lists -> device CSR ------------------------- */
@@ -218,13 +221,14 @@ int32_t ruvgnn_differentiable_search(ruvgnn_ctx *ctx, const float *queries, uint
  * (cur + aggregated)/2, cur = layers[l].forward(combined, selected rows, weights).
  * level_dim[l] must equal the current width and layers[l].input_dim
  * (RUVGNN_ERR_DIMENSION_MISMATCH; the reference panics inside ndarray).
- * out: [n_queries][width after the last applied layer]; *out_dim receives that width.
- * Host pointers only. */
+ * out: [n_queries][width after the last applied layer], out_capacity_floats = the TOTAL number
+ * of floats `out` can hold (>= n_queries * final width, else RUVGNN_ERR_INVALID_INPUT and *out_dim
+ * still receives the width); *out_dim receives that width.  Host pointers only. */
 int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *ctx, const float *queries, uint64_t n_queries,
                                     uint32_t query_dim, const float *const *level_emb,
                                     const uint64_t *level_rows, const uint32_t *level_dim,
                                     const ruvgnn_layer *const *layers, uint32_t n_levels,
-                                    float *out, uint32_t out_capacity_floats, uint32_t *out_dim);
+                                    float *out, uint64_t out_capacity_floats, uint32_t *out_dim);
 
 /* ---- range-partitioned forward (one process per GPU) -------- */
 /* Phase A: project the partition's own rows; x is [n_local][input_dim]
@@ -263,6 +267,94 @@ int32_t ruvgnn_layer_expand_halo(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
 int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
                                       const ruvgnn_graph *graph, const float *halo_dev,
                                       uint64_t row_begin, uint64_t row_end, float *out_dev);
+
+/* Diagnostic form of the multi-pass gather the partitioned forward uses (below): the layer
+ * forward over a single-device graph with the neighbour list of every node processed in
+ * n_splits + 1 passes over the column ranges [0, splits[0]), [splits[0], splits[1]), ...,
+ * [splits[n_splits-1], n_cols), the online-softmax state carried from pass to pass.  Equals
+ * ruvgnn_layer_forward up to f32 summation order.  Device pointers only.  Needs the fast layout
+ * (hidden_dim % 128 == 0, heads | 32), else RUVGNN_ERR_INVALID_SHAPE. */
+int32_t ruvgnn_layer_forward_split(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
+                                   const ruvgnn_graph *graph, const float *x_dev, float *out_dev,
+                                   const uint64_t *splits, uint32_t n_splits);
+
+/* ---- range-partitioned forward inside the library ----------------------------
+ * One ruvgnn_dist per GPU: an NCCL communicator (libnccl.so.2 is loaded at run time; absent
+ * -> RUVGNN_ERR_NCCL) and a communication stream beside the ctx's compute stream.  The host
+ * program is either one process per GPU (ruvgnn_dist_unique_id on rank 0, shipped to the other
+ * ranks by any transport, then ruvgnn_dist_create everywhere) or one process with one host
+ * thread per GPU (ruvgnn_dist_create_all = ncclCommInitAll; every collective entry below must
+ * then be called by all ranks concurrently, one thread each).  The reference has no
+ * multi-device path; weights are replicated like its Clone-able layer
+ * (crates/ruvector-cli/src/mcp/gnn_cache.rs:183-188). */
+#define RUVGNN_NCCL_ID_BYTES 128
+typedef struct ruvgnn_dist ruvgnn_dist;
+typedef struct ruvgnn_partition ruvgnn_partition;
+
+int32_t ruvgnn_dist_unique_id(uint8_t *id /* [RUVGNN_NCCL_ID_BYTES] */);
+/* id == NULL with world > 1 makes a plan-only handle: ruvgnn_partition_create builds this rank's
+ * plan (what it needs from whom) without talking to anyone, ruvgnn_dist_forward is refused. */
+int32_t ruvgnn_dist_create(ruvgnn_ctx *ctx, const uint8_t *id, int32_t rank, int32_t world,
+                           ruvgnn_dist **out);
+/* ctxs[r] (one per device, distinct devices) becomes rank r; out: [world] handles. */
+int32_t ruvgnn_dist_create_all(ruvgnn_ctx *const *ctxs, int32_t world, ruvgnn_dist **out);
+void ruvgnn_dist_destroy(ruvgnn_dist *d);
+int32_t ruvgnn_dist_info(const ruvgnn_dist *d, int32_t *rank, int32_t *world);
+
+/* Collective.  This rank's rows of a range-partitioned graph: rank p owns the node range
+ * [bounds[p], bounds[p+1]); row_ptr [n_local+1], col_idx GLOBAL node ids, edge_w.  Builds the halo
+ * plan on the device: remote columns are de-duplicated (bitmap over the node ids + prefix
+ * popcount), every row keeps its neighbours in stored order with columns renamed to
+ * [own rows | halo slots], and the request lists are exchanged over NCCL.  When every rank needs
+ * >= 75% of all remote rows and the ranges are equal the plan switches to the dense plane (all-gather
+ * of the projected rows in row chunks); otherwise the sparse plane (pack + all-to-all-v). */
+#define RUVGNN_PART_DEVICE_PTRS 1u /* row_ptr / col_idx / edge_w are device pointers */
+#define RUVGNN_PART_FORCE_SPARSE 2u
+#define RUVGNN_PART_FORCE_DENSE 4u /* needs equal ranges */
+int32_t ruvgnn_partition_create(ruvgnn_dist *d, const uint64_t *bounds, const uint64_t *row_ptr,
+                                const uint32_t *col_idx, const float *edge_w, uint32_t flags,
+                                ruvgnn_partition **out);
+void ruvgnn_partition_destroy(ruvgnn_partition *p);
+typedef struct {
+  uint64_t n_local, n_total, n_edges;
+  uint64_t n_halo;        /* distinct remote rows this rank's rows reference */
+  uint64_t n_send;        /* rows peers asked this rank for (sparse plane) */
+  uint64_t remote_edges;  /* edges whose endpoint is remote */
+  uint64_t interior_rows; /* rows in the contiguous all-local runs (exact mode overlaps them) */
+  uint32_t dense;         /* 1: all-gather plane */
+  uint32_t chunks;        /* row chunks of the dense plane */
+} ruvgnn_partition_info;
+int32_t ruvgnn_partition_stats(const ruvgnn_partition *p, ruvgnn_partition_info *out);
+/* Host copies of the plan, for checks: the renamed columns [n_edges], the global ids of the halo
+ * rows in slot order [n_halo] (sparse plane), the own-local rows sent to peers [n_send], rows
+ * received from / sent to each peer [world] each.  Any pointer may be NULL. */
+int32_t ruvgnn_partition_download(const ruvgnn_partition *p, uint32_t *col_idx_local,
+                                  uint32_t *need_ids, uint32_t *send_idx, uint64_t *recv_counts,
+                                  uint64_t *send_counts);
+
+/* Collective.  One layer over the partition: x [n_local][input_dim] -> out [n_local][hidden_dim]
+ * (host pointers by default: H2D / D2H pipelined in row blocks; RUVGNN_FWD_DEVICE_PTRS: device).
+ *   default     project -> exchange on the communication stream || gather pass over the own-row
+ *               edges -> one gather pass per halo chunk as it lands (online-softmax state carried
+ *               in HBM) -> update.  Equals the single-GPU result up to f32 summation order.
+ *   RUVGNN_DIST_EXACT   single-pass gather after the whole halo has arrived, all-local row runs
+ *               first: every row goes through exactly the arithmetic of the single-GPU run
+ *               (bit-identical outputs). */
+#define RUVGNN_DIST_EXACT 16u
+int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *p, const ruvgnn_layer *layer,
+                            const float *x, float *out, uint32_t flags);
+typedef struct {
+  double bytes_sent, bytes_received; /* per forward, this rank */
+  float exposed_wait_ms;             /* compute stream stalled on the exchange (last forward) */
+  float exchange_ms;                 /* first collective enqueued -> last chunk landed (comm stream) */
+  uint32_t passes;                   /* gather passes of the last forward */
+  uint32_t exact;                    /* 1: the last forward ran the exact (single-pass) form */
+} ruvgnn_dist_stats;
+/* Synchronises the ctx stream. */
+int32_t ruvgnn_dist_last_stats(ruvgnn_dist *d, ruvgnn_dist_stats *out);
+/* Row chunks of the dense plane (1..16, default 4) for partitions created afterwards: the
+ * all-gather runs chunk by chunk and the overlapped forward runs one gather pass per chunk. */
+int32_t ruvgnn_dist_set_chunks(ruvgnn_dist *d, uint32_t chunks);
 
 #ifdef __cplusplus
 }

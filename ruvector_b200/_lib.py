@@ -48,6 +48,7 @@ SYMBOLS = {
     "ruvgnn_layer_json_normalize": (C.c_int32, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ruvgnn_layer_dims": (C.c_int32, [_vp, _u32p, _u32p, _u32p, c_float_p]),
     "ruvgnn_layer_set_mode": (C.c_int32, [_vp, C.c_uint32]),
+    "ruvgnn_layer_mode": (C.c_uint32, [_vp]),
     "ruvgnn_layer_destroy": (None, [_vp]),
     "ruvgnn_pack_neighbours": (C.c_int32, [C.c_uint64, C.POINTER(_vp), _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u32p, c_float_p]),
     "ruvgnn_hnsw_dump_open": (C.c_int32, [C.c_char_p, C.POINTER(_vp)]),
@@ -63,7 +64,7 @@ SYMBOLS = {
     "ruvgnn_stack_forward": (C.c_int32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.c_uint32, _vp, _vp, C.c_uint32]),
     "ruvgnn_layer_forward_node": (C.c_int32, [_vp, _vp, c_float_p, C.c_uint32, c_float_p, C.c_uint32, c_float_p, C.c_uint32, c_float_p]),
     "ruvgnn_differentiable_search": (C.c_int32, [_vp, c_float_p, C.c_uint64, c_float_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, _u32p, c_float_p, _u32p, C.c_uint32]),
-    "ruvgnn_hierarchical_forward": (C.c_int32, [_vp, c_float_p, C.c_uint64, C.c_uint32, C.POINTER(c_float_p), _u64p, _u32p, C.POINTER(_vp), C.c_uint32, c_float_p, C.c_uint32, _u32p]),
+    "ruvgnn_hierarchical_forward": (C.c_int32, [_vp, c_float_p, C.c_uint64, C.c_uint32, C.POINTER(c_float_p), _u64p, _u32p, C.POINTER(_vp), C.c_uint32, c_float_p, C.c_uint64, _u32p]),
     "ruvgnn_layer_project": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_project_rows": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64]),
     "ruvgnn_layer_halo_width": (C.c_uint32, [_vp]),
@@ -71,9 +72,40 @@ SYMBOLS = {
     "ruvgnn_layer_messages": (C.c_int32, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "ruvgnn_layer_expand_halo": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_aggregate_update": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
+    "ruvgnn_layer_forward_split": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _u64p, C.c_uint32]),
+    "ruvgnn_dist_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
+    "ruvgnn_dist_create": (C.c_int32, [_vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "ruvgnn_dist_create_all": (C.c_int32, [C.POINTER(_vp), C.c_int32, C.POINTER(_vp)]),
+    "ruvgnn_dist_destroy": (None, [_vp]),
+    "ruvgnn_dist_info": (C.c_int32, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ruvgnn_dist_set_chunks": (C.c_int32, [_vp, C.c_uint32]),
+    "ruvgnn_partition_create": (C.c_int32, [_vp, _u64p, _vp, _vp, _vp, C.c_uint32, C.POINTER(_vp)]),
+    "ruvgnn_partition_destroy": (None, [_vp]),
+    "ruvgnn_partition_stats": (C.c_int32, [_vp, _vp]),
+    "ruvgnn_partition_download": (C.c_int32, [_vp, _u32p, _u32p, _u32p, _u64p, _u64p]),
+    "ruvgnn_dist_forward": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32]),
+    "ruvgnn_dist_last_stats": (C.c_int32, [_vp, _vp]),
 }
 
+
+class PartitionInfo(C.Structure):
+    """ruvgnn_partition_info (include/ruvgnn.h)."""
+
+    _fields_ = [("n_local", C.c_uint64), ("n_total", C.c_uint64), ("n_edges", C.c_uint64), ("n_halo", C.c_uint64),
+                ("n_send", C.c_uint64), ("remote_edges", C.c_uint64), ("interior_rows", C.c_uint64),
+                ("dense", C.c_uint32), ("chunks", C.c_uint32)]
+
+
+class DistStats(C.Structure):
+    """ruvgnn_dist_stats (include/ruvgnn.h)."""
+
+    _fields_ = [("bytes_sent", C.c_double), ("bytes_received", C.c_double), ("exposed_wait_ms", C.c_float),
+                ("exchange_ms", C.c_float), ("passes", C.c_uint32), ("exact", C.c_uint32)]
+
 FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
+DIST_EXACT = 16
+PART_DEVICE_PTRS, PART_FORCE_SPARSE, PART_FORCE_DENSE = 1, 2, 4
+NCCL_ID_BYTES = 128
 GRAPH_PRENORMALIZED = 1
 MODE_FP32_SIMT, MODE_FP32_TC, MODE_TF32 = 0, 1, 2
 

@@ -8,7 +8,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libruvgnn.so"
-SOURCES = ["ffi.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "gemm_tc4.cu", "rowops.cu", "search.cu", "json.cc", "packer.cc", "hnswio.cc"]
+SOURCES = ["ffi.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "gemm_tc4.cu", "rowops.cu", "search.cu", "dist.cu", "json.cc", "packer.cc", "hnswio.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose:
             print((objdir / (src + ".log")).read_text())
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs)]
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs), "-ldl"]
         subprocess.run(cmd, check=True)
     stamp.write_text(want)
     return LIB

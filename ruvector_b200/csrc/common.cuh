@@ -96,6 +96,13 @@ struct GatherArgs {
   uint64_t row_begin = 0, row_end = 0;
   uint32_t H = 0, heads = 0;
   int prenormalized = 0;
+  // Multi-pass gather (partitioned forward, dist.cu): this launch handles only the edges whose
+  // column lies in [col_lo, col_hi).  first: the state starts from zero; otherwise it is read
+  // back from oa (raw accumulators o | agg) and ml ([row][2*heads]: running max, running sum per
+  // head).  last: oa receives the normalised o | agg that K-upd reads; otherwise the raw state.
+  int multipass = 0, first = 1, last = 1;
+  uint64_t col_lo = 0, col_hi = ~0ull;
+  float *ml = nullptr;
 };
 cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
                           uint64_t *launches);
@@ -119,6 +126,10 @@ struct GatherR1Args {
   uint64_t row_begin = 0, row_end = 0;
   uint32_t heads = 0;
   int prenormalized = 0;
+  // multi-pass gather, as in GatherArgs (state: sa raw S_g | agg, ml [row][2*heads])
+  int multipass = 0, first = 1, last = 1;
+  uint64_t col_lo = 0, col_hi = ~0ull;
+  float *ml = nullptr;
 };
 cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s, uint64_t *launches);
 

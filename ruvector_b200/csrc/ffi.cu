@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "gemm_tc.cuh"
 #include "layer_host.h"
 #include "abi_guard.h"
+#include "engine.h"
 
 namespace ruvgnn {
 
@@ -26,77 +28,6 @@ int32_t fail(int32_t code, const std::string &msg) {
 }  // namespace ruvgnn
 
 using namespace ruvgnn;
-
-struct ruvgnn_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int sm_count = 148;      // SMs grids are sized for (ruvgnn_ctx_set_sm_limit)
-  int sm_count_dev = 148;  // SMs of the device
-  uint64_t launches = 0;
-  // activation workspace: P[n][4H] | OA[n][2H] | T0..T3[n][H]
-  float *ws = nullptr;
-  size_t ws_floats = 0;
-  // host-pointer staging
-  float *x_stage = nullptr, *out_stage = nullptr;
-  size_t x_stage_floats = 0, out_stage_floats = 0;
-  float *stack_buf[2] = {nullptr, nullptr};  // ping-pong activations of ruvgnn_stack_forward
-  size_t stack_floats[2] = {0, 0};
-  int *d_flag = nullptr;
-  // timing ring: every timed forward records 7 events into the next slot;
-  // ruvgnn_ctx_last_timing averages the slots recorded since the previous query.
-  // events: 0 start, 1 after h2d, 2 after project, 6 aggregate start (after the halo
-  // exchange in the partitioned path), 3 after gather, 4 after update, 5 after d2h
-  static constexpr int kRing = 32;
-  cudaEvent_t ring[kRing][7] = {};
-  // (start, end) event pairs around every K-agg launch of a slot (a forward may run K-agg once
-  // per row block / row range); created on first use
-  std::vector<cudaEvent_t> agg_ev[kRing];
-  uint32_t agg_used[kRing] = {};
-  int cur_slot = 0;
-  bool timing_on = false;  // ruvgnn_ctx_set_timing: also time project / aggregate_update
-  // host-buffer forward: copy streams + per-block events for the H2D | compute | D2H pipeline
-  static constexpr int kMaxBlocks = 16;
-  cudaStream_t s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[kMaxBlocks] = {}, ev_out[kMaxBlocks] = {}, ev_start = nullptr, ev_done = nullptr;
-  cudaEvent_t *ev = ring[0];
-  uint32_t ring_count = 0;
-  bool timing_valid = false;
-  // state of the last ruvgnn_layer_project
-  uint64_t proj_rows = 0;
-  uint32_t proj_H = 0;
-};
-
-struct ruvgnn_layer {
-  LayerHost host;  // logical layout, for to_json and re-upload
-  uint32_t D = 0, H = 0, heads = 0;
-  uint32_t mode = RUVGNN_MODE_FP32_SIMT;
-  bool fast = false;
-  ColumnOrder ord;
-  int device = 0;
-  float *blob = nullptr;  // one allocation, pointers below point inside
-  float *Wmsg = nullptr, *bmsg = nullptr;  // [H][D]
-  float *Wqkv = nullptr, *bqkv = nullptr;  // [3H][H]
-  float *Wo = nullptr, *bo = nullptr;      // [H][H]
-  float *Wagg = nullptr, *bagg = nullptr;  // [H][H]
-  float *Wzr = nullptr, *bzr = nullptr;    // [2H][2H]: rows z|r, cols a|m
-  float *Wh = nullptr, *bh = nullptr;      // [H][2H]: cols a|rh
-  float *gamma = nullptr, *beta = nullptr;
-  // R = 1 gather formulation (H == 128, heads in {1,2,4,8}; see GatherR1Args): folded weights
-  bool r1 = false;
-  float *Wqk = nullptr, *bqk = nullptr;  // [heads*H][H]: Qt_g = W_k[g]^T (W_q[g] m + b_q[g])
-  float *Wov = nullptr, *bov = nullptr;  // [H][heads*H]: attn = sum_g (W_o[:,g] W_v[g]) S_g + W_o b_v + b_o
-  TcWeights tc;  // split (hi/lo) copies for the tcgen05 path; empty unless usable
-};
-
-struct ruvgnn_graph {
-  int device = 0;
-  uint64_t n_nodes = 0, n_cols = 0, n_edges = 0;
-  uint32_t flags = 0;
-  uint64_t *row_ptr = nullptr;
-  uint32_t *col_idx = nullptr;
-  float *edge_w = nullptr;
-};
 
 namespace {
 
@@ -120,29 +51,16 @@ int32_t check_config(uint32_t input_dim, uint32_t hidden_dim, uint32_t heads, fl
   return RUVGNN_OK;
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) {
-      ok = false;
-      prev = -1;
-    }
-    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    if (!ok) cudaGetLastError();
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
+}  // namespace
 
-// floats per node of activation workspace: R=3: P(4H) OA(2H) T0..T3(4H); R=1: M(H) Qt(hH)
-// SA((h+1)H) T0..T3(4H)
+namespace ruvgnn {
+
 // Activation workspace.  Per node (kept for the whole forward, the gather reads them at arbitrary
 // rows): P[n][4H] = Q|K|V|M (R = 3) or M[n][H] + Qt[n][hH] (R = 1).  Per row block of at most
 // upd_block() rows (reused block after block by K-agg -> K-upd): OA[B][2H] or SA[B][(h+1)H], and
 // T0..T3[B][H].  1M nodes x 384: 6.1 + 9.2 GB; 10M nodes x 128 (R = 1, 4 heads): 25.6 + 4.8 GB
-// instead of 71.7 GB with everything per node.
+// instead of 71.7 GB with everything per node.  With ctx->state_per_node (multi-pass gather of the
+// partitioned forward) OA / SA cover all n rows and ML[n][2 heads] holds the running softmax state.
 uint64_t upd_block() {
   static uint64_t b = 0;
   if (!b) {
@@ -152,11 +70,13 @@ uint64_t upd_block() {
   }
   return b;
 }
-uint32_t ws_node_units(const ruvgnn_layer *L) { return L->r1 ? 1 + L->heads : 4; }
-uint32_t ws_block_units(const ruvgnn_layer *L) { return L->r1 ? L->heads + 5 : 6; }
-size_t ws_floats_needed(const ruvgnn_layer *L, uint64_t n) {
+static uint32_t ws_node_units(const ruvgnn_layer *L) { return L->r1 ? 1 + L->heads : 4; }
+static uint32_t ws_state_units(const ruvgnn_layer *L) { return L->r1 ? L->heads + 1 : 2; }
+size_t ws_floats_needed(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
   const uint64_t B = n < upd_block() ? n : upd_block();
-  return (size_t)n * L->H * ws_node_units(L) + (size_t)B * L->H * ws_block_units(L) + 64;
+  const uint64_t S = c->state_per_node ? n : B;
+  return (size_t)n * L->H * ws_node_units(L) + (size_t)S * L->H * ws_state_units(L) +
+         (size_t)B * L->H * 4 + (c->state_per_node ? (size_t)n * 2 * L->heads : 0) + 64;
 }
 
 int32_t ensure_ws_floats(ruvgnn_ctx *c, size_t need) {
@@ -167,12 +87,13 @@ int32_t ensure_ws_floats(ruvgnn_ctx *c, size_t need) {
     c->ws = nullptr;
     c->ws_floats = 0;
   }
+  invalidate_projection(c);
   RUVGNN_CUDA_TRY(cudaMalloc(&c->ws, need * sizeof(float)));
   c->ws_floats = need;
   return RUVGNN_OK;
 }
 int32_t ensure_ws(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
-  return ensure_ws_floats(c, ws_floats_needed(L, n));
+  return ensure_ws_floats(c, ws_floats_needed(c, L, n));
 }
 
 int32_t ensure_stage(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
@@ -188,17 +109,6 @@ int32_t ensure_stage(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
   return RUVGNN_OK;
 }
 
-struct Ws {
-  float *P, *OA, *T0, *T1, *T2, *T3;
-  int64_t ldp;
-  // views shared by both formulations
-  float *m;      // message rows (hidden state of the GRU)
-  int64_t ldm;
-  float *halo_src;  // rows a peer needs: K|V|M (3H) or M (H)
-  uint32_t halo_w;
-  // R = 1 only
-  float *Qt, *SA;
-};
 void begin_timing_slot(ruvgnn_ctx *c) {
   c->cur_slot = (int)(c->ring_count % ruvgnn_ctx::kRing);
   c->ev = c->ring[c->cur_slot];
@@ -206,15 +116,28 @@ void begin_timing_slot(ruvgnn_ctx *c) {
   ++c->ring_count;
 }
 
+void invalidate_projection(ruvgnn_ctx *c) {
+  c->proj_rows = 0;
+  c->proj_layer = nullptr;
+  c->proj_done_rows = 0;
+}
+// Is the workspace a projection of exactly this layer over n rows, carved the way the caller
+// is about to carve it?  all_rows: every row has been projected.
+bool projection_ready(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, bool all_rows) {
+  return c->proj_layer == L && c->proj_generation == L->generation && c->proj_rows == n && n > 0 &&
+         c->proj_state_rows == c->state_per_node && (!all_rows || c->proj_done_rows >= n);
+}
+
 Ws carve(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
   const uint32_t H = L->H;
   const uint64_t B = n < upd_block() ? n : upd_block();
+  const uint64_t S = c->state_per_node ? n : B;  // rows of gather state
   Ws w{};
   if (!L->r1) {
     w.P = c->ws;
     w.ldp = 4 * (int64_t)H;
-    w.OA = w.P + (size_t)n * 4 * H;  // block-local from here on
-    w.T0 = w.OA + (size_t)B * 2 * H;
+    w.OA = w.P + (size_t)n * 4 * H;
+    w.T0 = w.OA + (size_t)S * 2 * H;  // block-local from here on
     w.m = w.P + 3 * H;
     w.ldm = w.ldp;
     w.halo_src = w.P + H;
@@ -224,20 +147,24 @@ Ws carve(const ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n) {
     w.m = c->ws;
     w.ldm = H;
     w.Qt = w.m + (size_t)n * H;
-    w.SA = w.Qt + (size_t)n * h * H;  // block-local from here on
-    w.T0 = w.SA + (size_t)B * (h + 1) * H;
+    w.SA = w.Qt + (size_t)n * h * H;
+    w.T0 = w.SA + (size_t)S * (h + 1) * H;  // block-local from here on
     w.halo_src = w.m;
     w.halo_w = H;
   }
   w.T1 = w.T0 + (size_t)B * H;
   w.T2 = w.T1 + (size_t)B * H;
   w.T3 = w.T2 + (size_t)B * H;
+  w.ML = c->state_per_node ? w.T3 + (size_t)B * H : nullptr;
   return w;
 }
 
 // One GEMM of the layer, dispatched on the layer's arithmetic mode.
-int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKind epi, int which) {
-  if (L->mode != RUVGNN_MODE_FP32_SIMT && L->tc.usable) {
+static int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKind epi,
+                        int which) {
+  if (L->mode != RUVGNN_MODE_FP32_SIMT) {
+    if (!L->tc.usable)
+      return fail(RUVGNN_ERR_INVALID_SHAPE, "tensor-core mode on a layer without tensor-core weights");
     RUVGNN_CUDA_TRY(
         launch_gemm_tc(g, epi, L->tc, which, L->mode == RUVGNN_MODE_TF32, c->sm_count, c->stream,
                        &c->launches));
@@ -250,11 +177,20 @@ int32_t run_gemm(ruvgnn_ctx *c, const ruvgnn_layer *L, const GemmArgs &g, EpiKin
 // Phase A (K-proj): M = X W_msg^T + b (layer.rs:392-396, once per node instead of once
 // per edge), then Q|K|V = M [W_q;W_k;W_v]^T + b (:135-137).
 // Projects rows [rb, re) of an n-row partition (x_dev is the base of all n rows).
+// stages: 1 = the message GEMM, 2 = the query (Q|K|V) GEMM, 3 = both.  The partitioned forward
+// runs them apart when the halo rows are the message rows, so the exchange starts earlier.
 int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev,
-                        uint64_t rb, uint64_t re) {
+                        uint64_t rb, uint64_t re, int stages) {
   const uint32_t H = L->H, D = L->D;
   int32_t rc = ensure_ws(c, L, n);
   if (rc) return rc;
+  if (!projection_ready(c, L, n, false) || (rb == 0 && (stages & 1))) {  // a new projection starts
+    c->proj_rows = n;
+    c->proj_layer = L;
+    c->proj_generation = L->generation;
+    c->proj_state_rows = c->state_per_node;
+    c->proj_done_rows = 0;
+  }
   if (re <= rb) return RUVGNN_OK;
   Ws w = carve(c, L, n);
   GemmArgs g;
@@ -267,7 +203,8 @@ int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const 
   g.bias = L->bmsg;
   g.out = w.m + rb * w.ldm;
   g.ldo = w.ldm;
-  if ((rc = run_gemm(c, L, g, EPI_BIAS, TC_W_MSG))) return rc;
+  if ((stages & 1) && (rc = run_gemm(c, L, g, EPI_BIAS, TC_W_MSG))) return rc;
+  if (!(stages & 2)) return RUVGNN_OK;
   GemmArgs q;
   q.M = (int64_t)(re - rb);
   q.K1 = (int32_t)H;
@@ -287,30 +224,24 @@ int32_t do_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const 
     q.ldo = (int64_t)L->heads * H;
   }
   if ((rc = run_gemm(c, L, q, EPI_BIAS, TC_W_QKV))) return rc;
-  c->proj_rows = n;
-  c->proj_H = H;
+  c->proj_done_rows += re - rb;
   return RUVGNN_OK;
 }
 int32_t do_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n, const float *x_dev) {
-  return do_project_rows(c, L, n, x_dev, 0, n);
+  return do_project_rows(c, L, n, x_dev, 0, n, 3);
 }
 
-// Phase B: K-agg over rows [rb,re), then K-upd (out-proj + combine + W_agg, GRU,
-// dropout scale, LayerNorm; layer.rs:156-159,407-417).
-int32_t aggregate_update_block(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
-                               const float *halo, uint64_t rb, uint64_t re, float *out_dev,
-                               bool stage_events) {
+// K-agg over rows [rb, re): one pass of the gather (GatherPass).  The gather state of row r lives
+// at index r - sb of OA / SA, where sb is the first row of the current row block (0 when the state
+// is kept per node).
+int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, const float *halo,
+                    uint64_t rb, uint64_t re, const GatherPass &pass, bool stage_events) {
   const uint32_t H = L->H;
   const uint64_t n = c->proj_rows;
+  if (!pass.whole() && !c->state_per_node)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "multi-pass gather needs per-node gather state");
   Ws w = carve(c, L, n);
-  // OA / SA / T0..T3 hold rows [rb, re) only: row r of the block lives at index r - rb.  The
-  // kernels and GEMM arguments below index them by the node's row, so shift the bases once.
-  w.OA -= (ptrdiff_t)(rb * 2 * H);
-  if (L->r1) w.SA -= (ptrdiff_t)(rb * (uint64_t)(L->heads + 1) * H);
-  w.T0 -= (ptrdiff_t)(rb * H);
-  w.T1 -= (ptrdiff_t)(rb * H);
-  w.T2 -= (ptrdiff_t)(rb * H);
-  w.T3 -= (ptrdiff_t)(rb * H);
+  const uint64_t sb = c->state_per_node ? 0 : rb;
   cudaEvent_t agg_end = nullptr;
   if (c->timing_valid && stage_events) {
     std::vector<cudaEvent_t> &pool = c->agg_ev[c->cur_slot];
@@ -334,12 +265,18 @@ int32_t aggregate_update_block(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgn
     ga.row_ptr = G->row_ptr;
     ga.col_idx = G->col_idx;
     ga.edge_w = G->edge_w;
-    ga.oa = w.OA;
+    ga.oa = w.OA - (ptrdiff_t)(sb * 2 * H);
     ga.row_begin = rb;
     ga.row_end = re;
     ga.H = H;
     ga.heads = L->heads;
     ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+    ga.multipass = pass.whole() ? 0 : 1;
+    ga.col_lo = pass.col_lo;
+    ga.col_hi = pass.col_hi;
+    ga.first = pass.first ? 1 : 0;
+    ga.last = pass.last ? 1 : 0;
+    ga.ml = w.ML;
     RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
   } else {
     GatherR1Args ga;
@@ -351,18 +288,43 @@ int32_t aggregate_update_block(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgn
     ga.row_ptr = G->row_ptr;
     ga.col_idx = G->col_idx;
     ga.edge_w = G->edge_w;
-    ga.sa = w.SA;
+    ga.sa = w.SA - (ptrdiff_t)(sb * (uint64_t)(L->heads + 1) * H);
     ga.row_begin = rb;
     ga.row_end = re;
     ga.heads = L->heads;
     ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+    ga.multipass = pass.whole() ? 0 : 1;
+    ga.col_lo = pass.col_lo;
+    ga.col_hi = pass.col_hi;
+    ga.first = pass.first ? 1 : 0;
+    ga.last = pass.last ? 1 : 0;
+    ga.ml = w.ML;
     RUVGNN_CUDA_TRY(launch_gather_r1(ga, c->sm_count, c->stream, &c->launches));
   }
   if (agg_end) {
     cudaEventRecord(agg_end, c->stream);
     cudaEventRecord(c->ev[3], c->stream);
   }
+  return RUVGNN_OK;
+}
 
+// K-upd over rows [rb, re), re - rb <= upd_block(): out-proj + combine + W_agg, GRU, dropout
+// scale, LayerNorm (layer.rs:156-159,407-417).
+int32_t update_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, uint64_t rb,
+                    uint64_t re, float *out_dev) {
+  const uint32_t H = L->H;
+  const uint64_t n = c->proj_rows;
+  Ws w = carve(c, L, n);
+  // T0..T3 hold rows [rb, re) only (row r at index r - rb); OA / SA likewise unless the gather
+  // state is kept per node.  The GEMM arguments below index them by the node's row, so shift
+  // the bases once.
+  const uint64_t sb = c->state_per_node ? 0 : rb;
+  w.OA -= (ptrdiff_t)(sb * 2 * H);
+  if (L->r1) w.SA -= (ptrdiff_t)(sb * (uint64_t)(L->heads + 1) * H);
+  w.T0 -= (ptrdiff_t)(rb * H);
+  w.T1 -= (ptrdiff_t)(rb * H);
+  w.T2 -= (ptrdiff_t)(rb * H);
+  w.T3 -= (ptrdiff_t)(rb * H);
   const int64_t rows = (int64_t)(re - rb);
   const float *m = w.m + rb * w.ldm;
   int32_t rc;
@@ -432,15 +394,20 @@ int32_t aggregate_update_block(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgn
 // Phase B over rows [rb, re): one K-agg -> K-upd pass per block of at most upd_block() rows.
 int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
                             const float *halo, uint64_t rb, uint64_t re, float *out_dev,
-                            bool stage_events = true) {
+                            bool stage_events, const GatherPass &pass) {
   const uint64_t B = upd_block();
   for (uint64_t b0 = rb; b0 < re; b0 += B) {
     const uint64_t b1 = b0 + B < re ? b0 + B : re;
-    int32_t rc = aggregate_update_block(c, L, G, halo, b0, b1, out_dev, stage_events);
+    int32_t rc = gather_rows(c, L, G, halo, b0, b1, pass, stage_events);
+    if (!rc) rc = update_rows(c, L, G, b0, b1, out_dev);
     if (rc) return rc;
   }
   return RUVGNN_OK;
 }
+
+}  // namespace ruvgnn
+
+namespace {
 
 // Builds the device image of a layer: permuted / concatenated weights.
 int32_t upload_layer(ruvgnn_layer *L) {
@@ -601,6 +568,8 @@ int32_t make_layer(ruvgnn_ctx *ctx, std::unique_ptr<ruvgnn_layer> L, ruvgnn_laye
   L->H = L->host.hidden_dim;
   L->heads = L->host.heads;
   L->device = ctx->device;
+  static std::atomic<uint64_t> next_generation{1};
+  L->generation = next_generation.fetch_add(1);
   DeviceGuard dg(ctx->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   rc = upload_layer(L.get());
@@ -609,6 +578,10 @@ int32_t make_layer(ruvgnn_ctx *ctx, std::unique_ptr<ruvgnn_layer> L, ruvgnn_laye
     tc_weights_destroy(&L->tc);
     return rc;
   }
+  // Default arithmetic: the tcgen05 FP32-grade path (3xTF32) wherever the shape allows it, so a
+  // drop-in caller that never touches ruvgnn_layer_set_mode gets the measured path; FP32 FFMA
+  // only for shapes the tensor-core kernels do not cover (e.g. the reference's 4 -> 8 unit test).
+  L->mode = L->tc.usable ? RUVGNN_MODE_FP32_TC : RUVGNN_MODE_FP32_SIMT;
   *out = L.release();
   return RUVGNN_OK;
 }
@@ -618,7 +591,7 @@ int32_t make_layer(ruvgnn_ctx *ctx, std::unique_ptr<ruvgnn_layer> L, ruvgnn_laye
 extern "C" {
 
 const char *ruvgnn_last_error(void) { return g_last_error.c_str(); }
-uint32_t ruvgnn_abi_version(void) { return 1; }
+uint32_t ruvgnn_abi_version(void) { return 2; }
 
 int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
   RUVGNN_ABI_TRY
@@ -853,10 +826,14 @@ int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode) {
   if (mode > RUVGNN_MODE_TF32) return fail(RUVGNN_ERR_INVALID_INPUT, "unknown mode");
   if (mode != RUVGNN_MODE_FP32_SIMT && !layer->tc.usable)
     return fail(RUVGNN_ERR_INVALID_SHAPE,
-                "tensor-core modes need input_dim % 32 == 0 and hidden_dim % 64 == 0");
+                "tensor-core modes need input_dim % 32 == 0 and hidden_dim % 32 == 0");
   layer->mode = mode;
   return RUVGNN_OK;
   RUVGNN_ABI_CATCH
+}
+
+uint32_t ruvgnn_layer_mode(const ruvgnn_layer *layer) {
+  return layer ? layer->mode : RUVGNN_MODE_FP32_SIMT;
 }
 
 void ruvgnn_layer_destroy(ruvgnn_layer *L) {
@@ -964,9 +941,11 @@ int32_t ruvgnn_graph_download(const ruvgnn_graph *g, uint64_t *row_ptr, uint32_t
 void ruvgnn_graph_destroy(ruvgnn_graph *g) {
   if (!g) return;
   DeviceGuard dg(g->device);
-  if (g->row_ptr) cudaFree(g->row_ptr);
-  if (g->col_idx) cudaFree(g->col_idx);
-  if (g->edge_w) cudaFree(g->edge_w);
+  if (g->owns) {
+    if (g->row_ptr) cudaFree(g->row_ptr);
+    if (g->col_idx) cudaFree(g->col_idx);
+    if (g->edge_w) cudaFree(g->edge_w);
+  }
   delete g;
 }
 
@@ -985,6 +964,7 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
   const bool timing = flags & RUVGNN_FWD_TIMING;
+  c->state_per_node = false;
   const float *x_dev = x;
   float *out_dev = out;
   int32_t rc;
@@ -1090,10 +1070,11 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
   c->timing_valid = false;
+  c->state_per_node = false;
   int32_t rc;
   size_t ws_need = 0;
   for (uint32_t l = 0; l < n_layers; ++l) {
-    const size_t f = ws_floats_needed(layers[l], n);
+    const size_t f = ws_floats_needed(c, layers[l], n);
     ws_need = f > ws_need ? f : ws_need;
   }
   if ((rc = ensure_ws_floats(c, ws_need))) return rc;
@@ -1181,6 +1162,7 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = c->timing_on;
+  c->state_per_node = false;
   if (c->timing_on) {
     begin_timing_slot(c);
     cudaEventRecord(c->ev[0], c->stream);
@@ -1201,6 +1183,7 @@ int32_t ruvgnn_layer_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = c->timing_on;
+  c->state_per_node = false;
   if (c->timing_on && row_begin == 0) {
     begin_timing_slot(c);
     cudaEventRecord(c->ev[0], c->stream);
@@ -1223,7 +1206,7 @@ int32_t ruvgnn_halo_pack(ruvgnn_ctx *c, const ruvgnn_layer *L, const uint32_t *i
   if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_idx == 0) return RUVGNN_OK;
   if (!idx_dev || !send_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
-  if (c->proj_rows == 0 || c->proj_H != L->H)
+  if (!projection_ready(c, L, c->proj_rows, true))
     return fail(RUVGNN_ERR_INVALID_INPUT, "ruvgnn_layer_project has not run for this layer");
   DeviceGuard dg(c->device);
   Ws w = carve(c, L, c->proj_rows);
@@ -1239,7 +1222,7 @@ int32_t ruvgnn_layer_messages(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t row
   if (!c || !L) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_rows == 0) return RUVGNN_OK;
   if (!out_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
-  if (c->proj_rows == 0 || c->proj_H != L->H)
+  if (!projection_ready(c, L, c->proj_rows, true))
     return fail(RUVGNN_ERR_INVALID_INPUT, "ruvgnn_layer_project has not run for this layer");
   if (row_begin + n_rows > c->proj_rows)
     return fail(RUVGNN_ERR_INVALID_INPUT, "row range out of bounds");
@@ -1292,9 +1275,9 @@ int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, cons
                                       float *out_dev) {
   RUVGNN_ABI_TRY
   if (!c || !L || !G || !out_dev) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
-  if (c->proj_rows != G->n_nodes || c->proj_H != L->H)
+  if (!projection_ready(c, L, G->n_nodes, true))
     return fail(RUVGNN_ERR_INVALID_INPUT,
-                "ruvgnn_layer_project must run first with n_local == graph rows");
+                "ruvgnn_layer_project must run first (this layer, every row, n_local == graph rows)");
   if (G->n_cols > G->n_nodes && !halo_dev)
     return fail(RUVGNN_ERR_INVALID_INPUT, "graph addresses halo rows but halo_dev is null");
   if (row_end > G->n_nodes || row_begin > row_end)
@@ -1408,7 +1391,7 @@ extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queri
                                                const uint32_t *level_dim,
                                                const ruvgnn_layer *const *layers,
                                                uint32_t n_levels, float *out,
-                                               uint32_t out_capacity_floats, uint32_t *out_dim) {
+                                               uint64_t out_capacity_floats, uint32_t *out_dim) {
   RUVGNN_ABI_TRY
   if (!c || !queries || !out || !out_dim) return fail(RUVGNN_ERR_INVALID_INPUT, "null argument");
   if (n_levels && (!level_emb || !level_rows || !level_dim || !layers))
@@ -1429,12 +1412,14 @@ extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queri
     width = layers[l]->H;
   }
   *out_dim = width;
-  if (out_capacity_floats < width)
-    return fail(RUVGNN_ERR_INVALID_INPUT, "out buffer is too small for the final width");
+  if (n_queries > 0xffffffffffffffffull / (width ? width : 1) ||
+      out_capacity_floats < n_queries * (uint64_t)width)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "out buffer is too small for n_queries x final width");
   if (n_queries == 0) return RUVGNN_OK;
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = false;
+  c->state_per_node = false;
   const uint64_t nq = n_queries;
   DevBuf cur, nxt;
   RUVGNN_CUDA_TRY(cur.alloc(nq * query_dim * sizeof(float)));

@@ -165,6 +165,163 @@ __global__ void __launch_bounds__(128) gather_fast_kernel(GatherArgs a, float in
   }
 }
 
+
+// ---- multi-pass variants (partitioned forward) --------------------------------------------
+// The partitioned forward splits a node's neighbour list by where the rows live (own rows,
+// then one column range per halo chunk as it arrives) and runs one gather pass per range while
+// the next chunk is still on the wire.  A pass handles the edges whose column lies in
+// [col_lo, col_hi), in stored order, and carries the online-softmax state (raw accumulators,
+// running max and running sum per head) to the next pass through oa / ml.  The merge is the same
+// rescaling the single-pass kernels apply edge by edge, so the result equals the single pass up
+// to f32 summation order (own tolerance, tests/test_gpu_multipass.py).
+//
+// Compaction: per 32-edge chunk the in-range lanes are counted with a ballot and the t-th
+// in-range edge is handed to slot t by shuffle (__fns), after which the unfiltered inner loops run
+// unchanged on the compacted (col, weight) list.
+__device__ __forceinline__ int compact32(bool in_range, uint32_t &col, float &w, int lane) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, in_range);
+  const int cnt = __popc(mask);
+  const uint32_t src = __fns(mask, 0, lane + 1);  // lane of the (lane+1)-th in-range edge
+  const uint32_t from = src < 32u ? src : 0u;
+  col = __shfl_sync(0xffffffffu, col, from);
+  w = __shfl_sync(0xffffffffu, w, from);
+  if (lane >= cnt) w = 0.f;
+  return cnt;
+}
+
+template <int P, int LH, int U>
+__global__ void __launch_bounds__(128) gather_fast_mp_kernel(GatherArgs a, float inv_scale) {
+  constexpr int H = 128 * P;
+  constexpr int V = 32 * P;  // float4 per H-row
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int heads = 32 / LH, head = lane / LH;
+
+  for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
+    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    float4 *orow = reinterpret_cast<float4 *>(a.oa + node * (uint64_t)(2 * H));
+    float *ml = a.ml + node * (uint64_t)(2 * heads);
+    if (beg == end) {  // no neighbours: zeros in every pass (the update takes the LN(m) path)
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 2 * P; ++i) orow[i * 32 + lane] = zero;
+      continue;
+    }
+    const float4 *qrow = reinterpret_cast<const float4 *>(a.P + node * (uint64_t)a.ldp);
+    float4 q[P], acc[P], ag[P];
+    float mx = -INFINITY, l = 0.f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) q[i] = ldg4(qrow + i * 32 + lane);
+    if (a.first) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        acc[i] = orow[i * 32 + lane];
+        ag[i] = orow[V + i * 32 + lane];
+      }
+      mx = ml[head];
+      l = ml[heads + head];
+    }
+    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
+
+    auto row_of = [&](uint32_t col) -> const float4 * {
+      return (uint64_t)col < a.n_local
+                 ? reinterpret_cast<const float4 *>(a.P + (uint64_t)col * a.ldp + H)
+                 : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * (3 * H));
+    };
+    auto load = [&](RowRegs<P> &r, const float4 *rp) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) r.k[i] = ldg4(rp + i * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < P; ++i) r.v[i] = ldg4(rp + V + i * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < P; ++i) r.m[i] = ldg4(rp + 2 * V + i * 32 + lane);
+    };
+    auto consume = [&](const RowRegs<P> &r, float what) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        part = fmaf(q[i].x, r.k[i].x, part);
+        part = fmaf(q[i].y, r.k[i].y, part);
+        part = fmaf(q[i].z, r.k[i].z, part);
+        part = fmaf(q[i].w, r.k[i].w, part);
+      }
+#pragma unroll
+      for (int o = LH / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const float s = part * inv_scale;
+      const float mnew = fmaxf(mx, s);
+      const float corr = expf(mx - mnew);
+      const float p = expf(s - mnew);
+      l = fmaf(l, corr, p);
+      mx = mnew;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        acc[i].x = fmaf(acc[i].x, corr, p * r.v[i].x);
+        acc[i].y = fmaf(acc[i].y, corr, p * r.v[i].y);
+        acc[i].z = fmaf(acc[i].z, corr, p * r.v[i].z);
+        acc[i].w = fmaf(acc[i].w, corr, p * r.v[i].w);
+        ag[i].x = fmaf(what, r.m[i].x, ag[i].x);
+        ag[i].y = fmaf(what, r.m[i].y, ag[i].y);
+        ag[i].z = fmaf(what, r.m[i].z, ag[i].z);
+        ag[i].w = fmaf(what, r.m[i].w, ag[i].w);
+      }
+    };
+
+    for (uint64_t c = beg; c < end; c += 32) {
+      const uint64_t e = c + lane;
+      uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
+      const bool inr = e < end && (uint64_t)my_col >= a.col_lo && (uint64_t)my_col < a.col_hi;
+      const int cnt = compact32(inr, my_col, my_w, lane);
+      int jj = 0;
+      for (; jj + U <= cnt; jj += U) {
+        RowRegs<P> r[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t col = __shfl_sync(0xffffffffu, my_col, jj + u);
+          w[u] = __shfl_sync(0xffffffffu, my_w, jj + u);
+          load(r[u], row_of(col));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(r[u], w[u]);
+      }
+      for (; jj < cnt; ++jj) {
+        RowRegs<P> r;
+        const uint32_t col = __shfl_sync(0xffffffffu, my_col, jj);
+        const float w = __shfl_sync(0xffffffffu, my_w, jj);
+        load(r, row_of(col));
+        consume(r, w);
+      }
+    }
+    if (a.last) {
+      const float inv_l = 1.0f / fmaxf(l, 1e-10f);  // sum_exp.max(1e-10) (:198)
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        orow[i * 32 + lane] =
+            make_float4(acc[i].x * inv_l, acc[i].y * inv_l, acc[i].z * inv_l, acc[i].w * inv_l);
+        orow[V + i * 32 + lane] = ag[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        orow[i * 32 + lane] = acc[i];
+        orow[V + i * 32 + lane] = ag[i];
+      }
+      if (lane % LH == 0) {
+        ml[head] = mx;
+        ml[heads + head] = l;
+      }
+    }
+  }
+}
+
 // Any H / head count (identity column order).  One warp per node, running
 // state in shared memory.  Correctness path for shapes the fast kernel does
 // not cover (e.g. the reference's 4->8, 2-head unit-test layer).
@@ -528,6 +685,132 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args 
   }
 }
 
+
+// Multi-pass form of gather_r1_batched_kernel (see gather_fast_mp_kernel): the state is the raw
+// S_g | agg rows in sa and (running max, running sum) per head in ml.
+template <int HEADS>
+__global__ void __launch_bounds__(32, 16) gather_r1_batched_mp_kernel(GatherR1Args a, float scale_log2) {
+  constexpr int H = 128, EB = 8, N = EB * HEADS, REP = 32 / N;
+  const int lane = threadIdx.x;
+  const uint64_t warp = blockIdx.x;
+  const uint64_t nwarps = gridDim.x;
+  const int my_slot = lane >> 2;
+  const int my_head = (lane / REP) % HEADS;
+  for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
+    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    float4 *srow = reinterpret_cast<float4 *>(a.sa + node * (uint64_t)((HEADS + 1) * H));
+    float *ml = a.ml + node * (uint64_t)(2 * HEADS);
+    if (beg == end) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g <= HEADS; ++g) srow[g * 32 + lane] = zero;
+      continue;
+    }
+    const float4 *qrow = reinterpret_cast<const float4 *>(a.Qt + node * (uint64_t)(HEADS * H));
+    float4 qt[HEADS], S[HEADS];  // slot g: head g ^ my_head
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f);
+    float mx = -INFINITY, lsum = 0.f;
+#pragma unroll
+    for (int g = 0; g < HEADS; ++g) {
+      const float4 q = ldg4(qrow + (g ^ my_head) * 32 + lane);
+      qt[g] = make_float4(q.x * scale_log2, q.y * scale_log2, q.z * scale_log2, q.w * scale_log2);
+      S[g] = a.first ? make_float4(0.f, 0.f, 0.f, 0.f) : srow[(g ^ my_head) * 32 + lane];
+    }
+    if (!a.first) {
+      ag = srow[HEADS * 32 + lane];
+      mx = ml[my_head];
+      lsum = (my_slot == 0) ? ml[HEADS + my_head] : 0.f;  // the sum is re-split over the edge slots
+    }
+    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
+    for (uint64_t c = beg; c < end; c += 32) {
+      const uint64_t e = c + lane;
+      uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
+      const bool inr = e < end && (uint64_t)my_col >= a.col_lo && (uint64_t)my_col < a.col_hi;
+      const int cnt = compact32(inr, my_col, my_w, lane);
+      for (int jj = 0; jj < cnt; jj += EB) {
+        float4 r[EB];  // slot u: edge jj + (u ^ my_slot)
+        if (jj + EB < cnt) {
+          const int nsrc = jj + EB + my_slot;
+          const uint32_t ncol = __shfl_sync(0xffffffffu, my_col, nsrc < cnt ? nsrc : cnt - 1);
+          const float *nrow = ((uint64_t)ncol >= a.n_local)
+                                  ? a.halo + ((uint64_t)ncol - a.n_local) * H
+                                  : a.M + (uint64_t)ncol * a.ldm;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nrow + (lane & 3) * 32));
+        }
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const int src = jj + (u ^ my_slot);
+          const uint32_t col = __shfl_sync(0xffffffffu, my_col, src < cnt ? src : cnt - 1);
+          const float4 *row =
+              (uint64_t)col < a.n_local
+                  ? reinterpret_cast<const float4 *>(a.M + (uint64_t)col * a.ldm)
+                  : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * H);
+          r[u] = ldg4(row + lane);
+        }
+        float s[N];
+#pragma unroll
+        for (int u = 0; u < EB; ++u)
+#pragma unroll
+          for (int g = 0; g < HEADS; ++g)
+            s[u * HEADS + g] = fmaf(qt[g].x, r[u].x, fmaf(qt[g].y, r[u].y, fmaf(qt[g].z, r[u].z, qt[g].w * r[u].w)));
+        float t = reduce_scatter_xor<N>(s);
+        if (jj + my_slot >= cnt) t = -INFINITY;
+        float bm = t;
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+        const float nm = fmaxf(mx, bm);  // finite: the step holds at least one edge
+        const float p = ex2_approx(t - nm);
+        const float corr = ex2_approx(mx - nm);
+        mx = nm;
+        lsum = fmaf(lsum, corr, p);
+#pragma unroll
+        for (int g = 0; g < HEADS; ++g) {
+          const float cg = g ? __shfl_xor_sync(0xffffffffu, corr, g * REP) : corr;
+          S[g].x *= cg; S[g].y *= cg; S[g].z *= cg; S[g].w *= cg;
+        }
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+#pragma unroll
+          for (int g = 0; g < HEADS; ++g) {
+            const float pug = (u | g) ? __shfl_xor_sync(0xffffffffu, p, (u * HEADS + g) * REP) : p;
+            S[g].x = fmaf(pug, r[u].x, S[g].x);
+            S[g].y = fmaf(pug, r[u].y, S[g].y);
+            S[g].z = fmaf(pug, r[u].z, S[g].z);
+            S[g].w = fmaf(pug, r[u].w, S[g].w);
+          }
+          const int wsrc = jj + (u ^ my_slot);
+          const float w = __shfl_sync(0xffffffffu, my_w, wsrc & 31);  // 0 beyond the compacted list
+          ag.x = fmaf(w, r[u].x, ag.x);
+          ag.y = fmaf(w, r[u].y, ag.y);
+          ag.z = fmaf(w, r[u].z, ag.z);
+          ag.w = fmaf(w, r[u].w, ag.w);
+        }
+      }
+    }
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);  // normaliser of my head: sum over the edge slots
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+    if (a.last) {
+#pragma unroll
+      for (int g = 0; g < HEADS; ++g) {
+        const float lg = g ? __shfl_xor_sync(0xffffffffu, lsum, g * REP) : lsum;
+        const float inv_l = 1.0f / fmaxf(lg, 1e-10f);
+        srow[(g ^ my_head) * 32 + lane] = make_float4(S[g].x * inv_l, S[g].y * inv_l, S[g].z * inv_l, S[g].w * inv_l);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < HEADS; ++g) srow[(g ^ my_head) * 32 + lane] = S[g];
+      if (my_slot == 0 && lane % REP == 0) {
+        ml[my_head] = mx;
+        ml[HEADS + my_head] = lsum;
+      }
+    }
+    srow[HEADS * 32 + lane] = ag;
+  }
+}
+
 template <int HEADS>
 cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, cudaStream_t s) {
   const uint64_t rows = a.row_end - a.row_begin;
@@ -540,6 +823,15 @@ cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, c
   if (batched < 0) {
     const char *e = getenv("RUVGNN_R1_BATCH");
     batched = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (a.multipass) {
+    if constexpr (HEADS <= 4) {
+      uint64_t warps = rows < (uint64_t)sm_count * 64 ? rows : (uint64_t)sm_count * 64;
+      gather_r1_batched_mp_kernel<HEADS><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+      return cudaGetLastError();
+    } else {
+      return cudaErrorNotSupported;
+    }
   }
   if constexpr (HEADS <= 4) {
     if (batched) {
@@ -572,6 +864,18 @@ cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cu
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return cudaSuccess;
   dim3 grid((unsigned)blocks), block(32 * wpb);
+  if (a.multipass) {
+    switch (32 / a.heads) {
+      case 32: gather_fast_mp_kernel<P, 32, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 16: gather_fast_mp_kernel<P, 16, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 8: gather_fast_mp_kernel<P, 8, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 4: gather_fast_mp_kernel<P, 4, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 2: gather_fast_mp_kernel<P, 2, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 1: gather_fast_mp_kernel<P, 1, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   switch (32 / a.heads) {
     case 32: gather_fast_kernel<P, 32, U><<<grid, block, 0, s>>>(a, inv_scale); break;
     case 16: gather_fast_kernel<P, 16, U><<<grid, block, 0, s>>>(a, inv_scale); break;
@@ -616,6 +920,7 @@ cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStre
       default: return cudaErrorInvalidValue;
     }
   }
+  if (a.multipass) return cudaErrorNotSupported;  // generic layouts: single-pass only
   const size_t per_warp = (size_t)(3 * a.H + 2 * a.heads) * sizeof(float);
   int wpb = (int)((size_t)(96 * 1024) / per_warp);
   if (wpb > 4) wpb = 4;

@@ -97,8 +97,23 @@ struct Parser {
       return expect(']');
     }
   }
-  // skip any value
+  // skip any value.  Nesting is bounded like serde_json's recursion limit (128) so a hostile
+  // document cannot overflow the stack.
+  int depth = 0;
+  struct DepthGuard {
+    int &d;
+    explicit DepthGuard(int &dd) : d(dd) { ++d; }
+    ~DepthGuard() { --d; }
+  };
+  bool literal(const char *word) {
+    const size_t n = strlen(word);
+    if ((size_t)(end - p) < n || memcmp(p, word, n) != 0) return false;
+    p += n;
+    return true;
+  }
   bool skip() {
+    DepthGuard guard(depth);
+    if (depth > 128) return fail("recursion limit exceeded");
     ws();
     if (p >= end) return fail("unexpected end");
     if (*p == '{') {
@@ -138,12 +153,12 @@ struct Parser {
       std::string s;
       return string(s);
     }
-    if (!strncmp(p, "true", 4)) { p += 4; return true; }
-    if (!strncmp(p, "false", 5)) { p += 5; return true; }
-    if (!strncmp(p, "null", 4)) { p += 4; return true; }
+    if (literal("true") || literal("false") || literal("null")) return true;
     float f;
     return number(f);
   }
+  // a shape entry: a non-negative integer that fits u32 (anything else is rejected before a cast)
+  static bool dim_ok(float d) { return d >= 0.f && d <= 4294967040.f && d == floorf(d); }
 
   // ndarray serde form {"v":1,"dim":[...],"data":[...]}
   bool ndarray(std::vector<float> &dim, std::vector<float> &data) {
@@ -182,7 +197,12 @@ struct Parser {
     }
     if (!have_dim || !have_data) return fail("ndarray representation needs dim and data");
     size_t prod = 1;
-    for (float d : dim) prod *= (size_t)d;
+    for (float d : dim) {
+      if (!dim_ok(d)) return fail("invalid dimension (must be a non-negative integer below 2^32)");
+      const size_t di = (size_t)d;
+      if (di && prod > data.size() / di + 1) return fail("data and dimension must match in size");
+      prod *= di;
+    }
     if (prod != data.size()) return fail("data and dimension must match in size");
     return true;
   }
@@ -298,12 +318,14 @@ std::string parse_layer_json(const char *json, size_t len, LayerHost &L) {
         float f;
         if (g == "num_heads") {
           if (!ps.number(f)) return false;
+          if (!Parser::dim_ok(f)) return ps.fail("num_heads must be a non-negative integer");
           L.heads = (uint32_t)f;
           have_heads = true;
           return true;
         }
         if (g == "head_dim") {
           if (!ps.number(f)) return false;
+          if (!Parser::dim_ok(f)) return ps.fail("head_dim must be a non-negative integer");
           head_dim = (uint32_t)f;
           return true;
         }

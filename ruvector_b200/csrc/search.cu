@@ -43,7 +43,7 @@ __device__ __forceinline__ bool before(float va, uint32_t ia, float vb, uint32_t
   return va > vb || (va == vb && ia < ib);
 }
 
-// One CTA per query.  dots: [n_queries][n] raw dot products, overwritten with similarities.
+// One CTA per query.  dots: [n_queries][n] raw dot products, overwritten with the soft weights.
 __global__ void __launch_bounds__(256) topk_softmax_kernel(float *dots, const float *qnorm,
                                                            const float *enorm, uint64_t n, int k,
                                                            float temperature, uint32_t *idx_out,
@@ -56,33 +56,15 @@ __global__ void __launch_bounds__(256) topk_softmax_kernel(float *dots, const fl
   float *row = dots + q * n;
   const float nq = qnorm[q];
 
-  Best b;
-  for (int j = 0; j < k; ++j) {
-    b.v[j] = -INFINITY;
-    b.i[j] = 0xffffffffu;
-  }
+  // pass A: similarities and their maximum (softmax, search.rs:29-44)
   float mx = -INFINITY;
   for (uint64_t c = tid; c < n; c += 256) {
     const float ne = enorm[c];
     const float sim = (nq == 0.f || ne == 0.f) ? 0.f : row[c] / (nq * ne);
     row[c] = sim;
-    mx = fmaxf(mx, sim);
-    if (before(sim, (uint32_t)c, b.v[k - 1], b.i[k - 1])) {  // insertion into the sorted list
-      int j = k - 1;
-      while (j > 0 && before(sim, (uint32_t)c, b.v[j - 1], b.i[j - 1])) {
-        b.v[j] = b.v[j - 1];
-        b.i[j] = b.i[j - 1];
-        --j;
-      }
-      b.v[j] = sim;
-      b.i[j] = (uint32_t)c;
-    }
+    mx = fmaxf(mx, sim);  // f32::max semantics: NaN is ignored
   }
   s_red[tid] = mx;
-  for (int j = 0; j < k; ++j) {
-    s_v[tid * KMAX + j] = b.v[j];
-    s_i[tid * KMAX + j] = b.i[j];
-  }
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if (tid < s) s_red[tid] = fmaxf(s_red[tid], s_red[tid + s]);
@@ -90,6 +72,7 @@ __global__ void __launch_bounds__(256) topk_softmax_kernel(float *dots, const fl
   }
   mx = s_red[0];
   __syncthreads();
+  // pass B: normaliser
   float sum = 0.f;
   for (uint64_t c = tid; c < n; c += 256) sum += expf((row[c] - mx) / temperature);
   s_red[tid] = sum;
@@ -99,6 +82,35 @@ __global__ void __launch_bounds__(256) topk_softmax_kernel(float *dots, const fl
     __syncthreads();
   }
   sum = fmaxf(s_red[0], 1e-10f);
+  __syncthreads();
+  // pass C: the k best by soft WEIGHT, ties in index order -- the reference sorts the weights
+  // with a stable sort (:79-87), so similarities whose weights round equal keep index order.
+  // A NaN weight (NaN / Inf in the embeddings) ranks lowest, so k slots are always filled.
+  Best b;
+  for (int j = 0; j < k; ++j) {
+    b.v[j] = -INFINITY;
+    b.i[j] = 0xffffffffu;
+  }
+  for (uint64_t c = tid; c < n; c += 256) {
+    const float w = expf((row[c] - mx) / temperature) / sum;
+    row[c] = w;
+    const float key = (w == w) ? w : -INFINITY;
+    if (before(key, (uint32_t)c, b.v[k - 1], b.i[k - 1])) {  // insertion into the sorted list
+      int j = k - 1;
+      while (j > 0 && before(key, (uint32_t)c, b.v[j - 1], b.i[j - 1])) {
+        b.v[j] = b.v[j - 1];
+        b.i[j] = b.i[j - 1];
+        --j;
+      }
+      b.v[j] = key;
+      b.i[j] = (uint32_t)c;
+    }
+  }
+  for (int j = 0; j < k; ++j) {
+    s_v[tid * KMAX + j] = b.v[j];
+    s_i[tid * KMAX + j] = b.i[j];
+  }
+  __syncthreads();
   if (tid == 0) {
     // k-way merge of the 256 sorted per-thread lists
     int head[256];
@@ -118,10 +130,14 @@ __global__ void __launch_bounds__(256) topk_softmax_kernel(float *dots, const fl
           bi = i;
         }
       }
-      if (bt < 0) break;
+      if (bt < 0) {  // cannot happen for k <= n; keep the outputs defined anyway
+        idx_out[q * k + j] = 0;
+        w_out[q * k + j] = 0.f;
+        continue;
+      }
       ++head[bt];
       idx_out[q * k + j] = bi;
-      w_out[q * k + j] = expf((bv - mx) / temperature) / sum;
+      w_out[q * k + j] = row[bi];
     }
   }
 }

@@ -1,13 +1,18 @@
 """Range-partitioned multi-GPU forward with halo exchange.
 
-One process per GPU (``torch.distributed``).  Nodes are split into contiguous ranges;
-rank p owns rows ``[bounds[p], bounds[p+1])`` of X and of the CSR, projects its own rows,
-and needs the projected K|V|M rows of every *remote* neighbour its rows reference.  Those
-are de-duplicated per peer once per graph (:class:`HaloPlan`, pure host logic) and moved
-once per layer with a single all-to-all-v over NCCL/NVLink into a halo buffer the
-gather kernel addresses as rows ``n_local + slot``.  Neighbour order inside every row is
-preserved (indices are remapped, never reordered), so a partitioned run performs exactly
-the per-row arithmetic of the single-GPU run.
+Nodes are split into contiguous ranges; rank p owns rows ``[bounds[p], bounds[p+1])`` of X
+and of the CSR, projects its own rows, and needs the projected rows of every *remote*
+neighbour its rows reference.  The product path lives in the library (``csrc/dist.cu``, C ABI
+``ruvgnn_dist_*`` / ``ruvgnn_partition_*``): NCCL communicator, halo plan built on the device,
+exchange on a communication stream overlapped with the gather passes that do not need it.
+:class:`Dist` and :class:`Partition` below are thin ``ctypes`` callers of it; there is no
+``torch.distributed`` call on the data path (the host program only ships the 128-byte NCCL id
+to the other ranks, by any transport it likes).
+
+:class:`HaloPlan` and the NumPy helpers are the host-side *model* of the plan the library
+builds on the device (de-duplicated remote columns grouped by owner, neighbour order inside
+every row preserved, dense-plane column map, interior runs).  The tests check the device plan
+against them, and the gloo tests exercise the same logic across processes on CPU.
 
 The reference has no multi-device path at all; weights (< 30 MB) are
 replicated, exactly like its ``Clone``-able layer (gnn_cache.rs:183-188).
@@ -200,220 +205,180 @@ def dense_columns(plan: HaloPlan, starts: Optional[np.ndarray] = None) -> np.nda
     return out.astype(np.uint32)
 
 
-class Partition:
-    """Device-side state of one rank: plan, device CSR, send indices, buffers.
+class Dist:
+    """``ruvgnn_dist``: this rank's NCCL communicator + communication stream (csrc/dist.cu)."""
 
-    Two data planes with identical results: ``sparse`` = pack the rows each peer asked for
-    and exchange them with one all-to-all-v; ``dense`` = copy the whole projected K|V|M
-    block contiguously and all-gather it (chosen collectively when the halo is almost
-    everything, see :func:`choose_dense`).
-
-    The dense plane moves message rows only (H floats instead of the 3H of K|V|M): the rows are
-    all-gathered in ``chunks`` pieces and K|V of each piece is rebuilt on arrival
-    (``ruvgnn_layer_expand_halo``, the projection's own GEMM, so the bits are the owner's) while
-    the next piece is still on the wire; during that phase the kernels' grids leave ``comm_sms``
-    SMs to the collective.
-
-    ``overlap``: the collective is issued asynchronously (NCCL runs it on its own stream) and
-    the interior row ranges (:func:`interior_runs`) are aggregated and updated while it is in
-    flight; the launching stream then waits for the halo and finishes the boundary ranges.
-    Each row sees exactly the same arithmetic either way."""
-
-    def __init__(self, plan: HaloPlan, ctx, dense: bool = False, overlap: bool = True, chunks: int = 4,
-                 comm_sms: Optional[int] = None):
-        import torch
-
-        from .graph import CsrGraph
-
-        self.plan, self.ctx, self.dense = plan, ctx, dense
-        import os
-
-        # SMs left to the collective while kernels run beside it.  Measured on 2 B200s: 0, 16 and 32 give the
-        # same step time (the GEMMs that run beside the exchange are L2-bandwidth-bound and so is the
-        # collective's copy, so they share that, not SMs) and capping NCCL's blocks costs bandwidth: default 0.
-        self.comm_sms = int(os.environ.get("RUVGNN_COMM_SMS", "0")) if comm_sms is None else int(comm_sms)
-        if dense:
-            n_total = int(plan.bounds[-1])
-            self.starts = chunk_starts(plan.n_local, chunks)
-            g = CsrGraph(plan.graph.row_ptr, dense_columns(plan, self.starts), plan.graph.edge_w)
-            self.graph = g.to_device(ctx, n_cols=plan.n_local + n_total)
-            self.send_idx = torch.zeros(0, dtype=torch.int32, device="cuda")
-        else:
-            self.graph = plan.graph.to_device(ctx, n_cols=plan.n_local + plan.n_halo)
-            self.send_idx = torch.from_numpy(plan.send_idx.astype(np.int64)).to(torch.int32).cuda().contiguous()
-        self._send = self._halo = self._x = self._out = self._s_in = self._s_out = None
-        self._ring = []
-        self.bytes_exchanged = 0
-        self.interior, self.boundary = interior_runs(plan) if overlap else ([], [(0, plan.n_local)] if plan.n_local else [])
-        self.interior_rows = sum(b - a for a, b in self.interior)
-        self._wait_ev = None
-        self.trace = None  # set to [] to collect (label, event) pairs of the next forward (diagnostics)
-
-    def _mark(self, label):
-        if self.trace is not None:
-            import torch
-
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            self.trace.append((label, ev))
-
-    def trace_ms(self):
-        """[(label, ms since the previous mark)] of the traced forward.  Synchronises."""
-        out = []
-        for (_, e0), (label, e1) in zip(self.trace, self.trace[1:]):
-            e1.synchronize()
-            out.append((label, round(float(e0.elapsed_time(e1)), 3)))
-        return out
-
-    @classmethod
-    def build(cls, local_rows: CsrGraph, rank: int, world: int, n_per_rank: int, ctx, overlap: bool = True) -> "Partition":
-        plan = exchange_requests(HaloPlan.build(local_rows, rank, even_bounds(n_per_rank * world, world)))
-        return cls(plan, ctx, dense=choose_dense(plan), overlap=overlap)
-
-    def exposed_wait_ms(self) -> float:
-        """Device time the launching stream spent waiting for the halo in the last forward
-        (the part of the exchange that interior compute did not hide).  Synchronises."""
-        if self._wait_ev is None:
-            return 0.0
-        self._wait_ev[1].synchronize()
-        return float(self._wait_ev[0].elapsed_time(self._wait_ev[1]))
-
-    def forward(self, layer, x_dev, out_dev, timing: bool = False):
-        """project -> pack -> exchange (NCCL, asynchronous) || interior rows -> boundary rows.
-        Enqueue only."""
-        self._forward(layer, x_dev, out_dev)
-
-    def _forward(self, layer, x_dev, out_dev, x_host=None, out_host=None, blocks: int = 8):
-        """Device buffers, or (``x_host`` / ``out_host`` given, pinned) the host-buffer pipeline: X is
-        copied in row blocks on a copy stream and each block is projected as it lands; each finished
-        row range of the output is copied back on a second copy stream while the next range computes."""
+    def __init__(self, ctx, rank: int = 0, world: int = 1, unique_id: Optional[bytes] = None):
         import ctypes as C
-
-        import torch
-        import torch.distributed as dist
 
         from . import _lib
 
-        lib, plan, H = _lib.load(), self.plan, layer.hidden_dim
-        h = layer._device_layer()
-        n = plan.n_local
-        main = torch.cuda.current_stream()
-        self._mark("start")
-        if x_host is None:
-            _lib.check(lib.ruvgnn_layer_project(self.ctx.handle, h, n, C.c_void_p(x_dev.data_ptr())))
+        self._lib = _lib.load()
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = C.c_void_p()
+        idbuf = None  # world > 1 without an id: plan-only handle (no communicator)
+        if world > 1 and unique_id is not None:
+            if len(unique_id) != _lib.NCCL_ID_BYTES:
+                raise ValueError("unique_id must be the 128 bytes ruvgnn_dist_unique_id() returned on rank 0")
+            idbuf = (C.c_uint8 * _lib.NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        _lib.check(self._lib.ruvgnn_dist_create(ctx.handle, idbuf, self.rank, self.world, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+
+        from . import _lib
+
+        buf = (C.c_uint8 * _lib.NCCL_ID_BYTES)()
+        _lib.check(_lib.load().ruvgnn_dist_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_env(cls, ctx, group=None) -> "Dist":
+        """One process per GPU under torchrun: rank 0 makes the NCCL id and ``torch.distributed``
+        (already initialised by the host program, any backend) carries it to the other ranks."""
+        import torch.distributed as dist
+
+        if not dist.is_available() or not dist.is_initialized():
+            return cls(ctx, 0, 1)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(ctx, rank, world, box[0])
+
+    def set_chunks(self, chunks: int):
+        """Row chunks of the dense plane, for partitions created afterwards."""
+        from . import _lib
+
+        _lib.check(self._lib.ruvgnn_dist_set_chunks(self.handle, int(chunks)))
+
+    def last_stats(self) -> dict:
+        import ctypes as C
+
+        from . import _lib
+
+        st = _lib.DistStats()
+        _lib.check(self._lib.ruvgnn_dist_last_stats(self.handle, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.ruvgnn_dist_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Partition:
+    """``ruvgnn_partition``: this rank's rows of a range-partitioned graph plus the halo plan the
+    library built for them on the device (collective constructor).
+
+    ``row_ptr`` / ``col_idx`` (GLOBAL node ids) / ``edge_w`` are NumPy arrays, or -- with
+    ``device_ptrs=True`` -- objects with ``data_ptr()`` (device tensors: ``row_ptr`` int64/uint64
+    ``[n_local+1]``, ``col_idx`` int32/uint32, ``edge_w`` float32).
+
+    ``forward`` / ``forward_host`` run one layer.  Default: the halo exchange overlaps a gather
+    pass over the own-row edges, then one pass per halo chunk as it lands (result equal to the
+    single-GPU run up to f32 summation order); ``exact=True``: single-pass gather after the halo
+    has arrived (bit-identical to the single-GPU run)."""
+
+    def __init__(self, dist_: Dist, bounds, row_ptr, col_idx, edge_w, device_ptrs: bool = False,
+                 plane: Optional[str] = None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib = _lib.load()
+        self.dist = dist_
+        self.bounds = np.ascontiguousarray(bounds, dtype=np.uint64)
+        if self.bounds.size != dist_.world + 1:
+            raise ValueError("bounds must have world + 1 entries")
+        flags = {None: 0, "sparse": _lib.PART_FORCE_SPARSE, "dense": _lib.PART_FORCE_DENSE}[plane]
+        if device_ptrs:
+            flags |= _lib.PART_DEVICE_PTRS
+            ptrs = [C.c_void_p(t.data_ptr()) for t in (row_ptr, col_idx, edge_w)]
+            self._keep = (row_ptr, col_idx, edge_w)
         else:
-            if self._s_in is None:
-                self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
-            self._s_in.wait_stream(main)
-            self._s_out.wait_stream(main)
-            edges = [(n * b) // blocks for b in range(blocks + 1)]
-            landed = []
-            with torch.cuda.stream(self._s_in):
-                for a, b in zip(edges, edges[1:]):
-                    if b > a:
-                        x_dev[a:b].copy_(x_host[a:b], non_blocking=True)
-                        landed.append((a, b, self._s_in.record_event()))
-            for a, b, ev in landed:
-                main.wait_event(ev)
-                _lib.check(lib.ruvgnn_layer_project_rows(self.ctx.handle, h, n, C.c_void_p(x_dev.data_ptr()), a, b))
-        self._mark("project")
-        W = int(lib.ruvgnn_layer_halo_width(h))  # 3H (K|V|M rows) or H (message rows, R=1 layers)
+            rp = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+            ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
+            ew = np.ascontiguousarray(edge_w, dtype=np.float32)
+            ptrs = [C.c_void_p(a.ctypes.data) for a in (rp, ci, ew)]
+            self._keep = (rp, ci, ew)
+        h = C.c_void_p()
+        _lib.check(self._lib.ruvgnn_partition_create(
+            dist_.handle, self.bounds.ctypes.data_as(C.POINTER(C.c_uint64)), *ptrs, flags, C.byref(h)))
+        self.handle = h
+        self._keep = None
+        info = _lib.PartitionInfo()
+        _lib.check(self._lib.ruvgnn_partition_stats(h, C.byref(info)))
+        self.info = {k: int(getattr(info, k)) for k, _ in info._fields_}
+        self.n_local, self.n_halo = self.info["n_local"], self.info["n_halo"]
+        self.dense, self.interior_rows = bool(self.info["dense"]), self.info["interior_rows"]
+        self._x = self._out = None
 
-        work, works = None, {}
-        if self.dense:
-            n_total, P = int(plan.bounds[-1]), plan.world
-            nchunks = len(self.starts) - 1
-            if self._send is None or self._send.shape != (n, H):
-                self._send = torch.empty((n, H), dtype=torch.float32, device=x_dev.device)
-                self._halo = torch.empty((n_total, W), dtype=torch.float32, device=x_dev.device)
-                # K|V|M halo rows: the gathered message rows pass through a 2-deep ring of chunk
-                # buffers; message-row halos (W == H) are gathered straight into place
-                big = int(np.diff(self.starts).max())
-                self._ring = [] if W == H else [torch.empty((P * big, H), dtype=torch.float32, device=x_dev.device)
-                                                for _ in range(min(2, nchunks))]
-            _lib.check(lib.ruvgnn_layer_messages(self.ctx.handle, h, 0, n, C.c_void_p(self._send.data_ptr())))
+    @classmethod
+    def from_graph(cls, dist_: Dist, local_rows: CsrGraph, n_per_rank: int, plane: Optional[str] = None) -> "Partition":
+        """Equal ranges of ``n_per_rank`` rows; ``local_rows`` holds this rank's rows, global columns."""
+        return cls(dist_, even_bounds(n_per_rank * dist_.world, dist_.world), local_rows.row_ptr,
+                   local_rows.col_idx, local_rows.edge_w, plane=plane)
 
-            def landing(c):
-                a, b = int(self.starts[c]), int(self.starts[c + 1])
-                return self._halo[P * a:P * b] if W == H else self._ring[c % 2][:P * (b - a)]
+    def download(self) -> dict:
+        """Host copies of the device plan (checks)."""
+        import ctypes as C
 
-            def issue(c):  # the collective starts after everything enqueued so far on this stream
-                a, b = int(self.starts[c]), int(self.starts[c + 1])
-                works[c] = dist.all_gather_into_tensor(landing(c), self._send[a:b], async_op=True)
+        i, world = self.info, self.dist.world
+        col = np.empty(i["n_edges"], np.uint32)
+        need = np.empty(0 if self.dense else i["n_halo"], np.uint32)
+        send = np.empty(i["n_send"], np.uint32)
+        rc, sc = np.empty(world, np.uint64), np.empty(world, np.uint64)
+        u32, u64 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+        from . import _lib
 
-            for c in range(nchunks if W == H else min(2, nchunks)):
-                issue(c)
-            self.bytes_exchanged = (n_total - n) * H * 4 * 2
-        else:
-            n_send = int(self.send_idx.numel())
-            if self._send is None or self._send.shape != (n_send, W):
-                self._send = torch.empty((n_send, W), dtype=torch.float32, device=x_dev.device)
-            if n_send:
-                _lib.check(lib.ruvgnn_halo_pack(self.ctx.handle, h, C.c_void_p(self.send_idx.data_ptr()), n_send,
-                                                C.c_void_p(self._send.data_ptr())))
-            if self._halo is None or self._halo.shape != (plan.n_halo, W):
-                self._halo = torch.empty((plan.n_halo, W), dtype=torch.float32, device=x_dev.device)
-            if plan.world > 1:
-                work = dist.all_to_all_single(self._halo, self._send, plan.recv_counts.tolist(),
-                                              plan.send_counts.tolist(), async_op=True)
-            self.bytes_exchanged = (n_send + plan.n_halo) * W * 4
-        halo_ptr = self._halo.data_ptr() if (plan.n_halo or self.dense) else None
-        step = max((n + blocks - 1) // blocks, 1) if out_host is not None else max(n, 1)
+        _lib.check(self._lib.ruvgnn_partition_download(
+            self.handle, col.ctypes.data_as(u32), need.ctypes.data_as(u32), send.ctypes.data_as(u32),
+            rc.ctypes.data_as(u64), sc.ctypes.data_as(u64)))
+        return {"col_idx": col, "need_ids": need, "send_idx": send, "recv_counts": rc, "send_counts": sc}
 
-        def rows(a, b):
-            for a0 in range(a, b, step):  # host pipeline: hand finished sub-ranges to the copy-out stream
-                b0 = min(a0 + step, b)
-                _lib.check(lib.ruvgnn_layer_aggregate_update(self.ctx.handle, h, self.graph.handle,
-                                                             C.c_void_p(halo_ptr), a0, b0, C.c_void_p(out_dev.data_ptr())))
-                if out_host is not None:
-                    self._s_out.wait_event(main.record_event())
-                    with torch.cuda.stream(self._s_out):
-                        out_host[a0:b0].copy_(out_dev[a0:b0], non_blocking=True)
+    def forward(self, layer, x_dev, out_dev, exact: bool = False, asynchronous: bool = True):
+        """Device buffers (objects with ``data_ptr()`` or raw pointers); enqueue only by default.
+        The work runs on the ctx stream (``ruvgnn_ctx_stream``): order the buffers against it."""
+        import ctypes as C
 
-        self._mark("pack")
-        limited = bool(works or work is not None) and self.comm_sms > 0
-        if limited:  # leave SMs to the collective: persistent grids must not queue behind its blocks
-            _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, -self.comm_sms))
-        for a, b in self.interior:  # no remote neighbour: runs while the collective is in flight
-            rows(a, b)
-        if self._wait_ev is None:
-            self._wait_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        self._wait_ev[0].record()
-        if work is not None:
-            work.wait()  # the launching stream waits for the halo; the host does not block
-        if self.dense:  # rebuild K|V of chunk c while chunk c+1 is on the wire
-            P, r = plan.world, plan.rank
-            for c in range(nchunks):
-                works[c].wait()
-                self._mark(f"wait{c}")
-                if W == H:
-                    continue
-                a, b = int(self.starts[c]), int(self.starts[c + 1])
-                src, dst = landing(c), self._halo[P * a:P * b]
-                for lo, hi in ((0, r * (b - a)), ((r + 1) * (b - a), P * (b - a))):  # skip own block
-                    if hi > lo:
-                        _lib.check(lib.ruvgnn_layer_expand_halo(self.ctx.handle, h, C.c_void_p(src[lo:hi].data_ptr()),
-                                                                hi - lo, C.c_void_p(dst[lo:hi].data_ptr())))
-                self._mark(f"expand{c}")
-                if c + 2 < nchunks:
-                    issue(c + 2)  # reuses this chunk's ring buffer: ordered after the rebuild just enqueued
-        self._wait_ev[1].record()
-        if limited:
-            _lib.check(lib.ruvgnn_ctx_set_sm_limit(self.ctx.handle, 0))
-        for a, b in self.boundary:
-            rows(a, b)
-        self._mark("boundary")
-        if out_host is not None:
-            main.wait_stream(self._s_out)
+        from . import _lib
 
-    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray):
-        """Host buffers in, host buffers out (H2D / D2H inside, pipelined against the projection and the
-        update when the buffers are pinned): the e2e leg of bench.py.  Blocks until the output is there."""
-        import torch
+        xp = x_dev.data_ptr() if hasattr(x_dev, "data_ptr") else int(x_dev)
+        op = out_dev.data_ptr() if hasattr(out_dev, "data_ptr") else int(out_dev)
+        flags = _lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.DIST_EXACT if exact else 0)
+        _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
+                                                 C.c_void_p(xp), C.c_void_p(op), flags))
 
-        xt, ot = torch.from_numpy(x_np), torch.from_numpy(out_np)
-        if self._x is None or self._x.shape != xt.shape:
-            self._x = torch.empty(xt.shape, dtype=torch.float32, device="cuda")
-            self._out = torch.empty(ot.shape, dtype=torch.float32, device="cuda")
-        self._forward(layer, self._x, self._out, x_host=xt, out_host=ot)
-        torch.cuda.current_stream().synchronize()
+    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray, exact: bool = False):
+        """Host buffers in, host buffers out (H2D / D2H inside the call, pipelined in row blocks when the
+        buffers are pinned): the e2e leg of bench.py.  Blocks until the output is there."""
+        import ctypes as C
+
+        from . import _lib
+
+        if x_np.dtype != np.float32 or out_np.dtype != np.float32 or not x_np.flags.c_contiguous or not out_np.flags.c_contiguous:
+            raise ValueError("x / out must be C-contiguous float32 arrays")
+        if x_np.shape != (self.n_local, layer.input_dim) or out_np.shape != (self.n_local, layer.hidden_dim):
+            raise ValueError("x must be [n_local, input_dim] and out [n_local, hidden_dim]")
+        _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
+                                                 C.c_void_p(x_np.ctypes.data), C.c_void_p(out_np.ctypes.data),
+                                                 _lib.DIST_EXACT if exact else 0))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.ruvgnn_partition_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -42,6 +42,20 @@ class Context:
         _lib.check(self._lib.ruvgnn_sync(self.handle))
 
     @property
+    def stream(self) -> int:
+        """The ``cudaStream_t`` every kernel of this ctx is enqueued on.  A ctx created without a
+        stream owns a non-blocking one, which does NOT synchronise with torch's current stream:
+        device buffers handed to the ``*_device`` entries must be ordered against THIS stream
+        (``torch_stream()``), or the ctx must be created on the caller's stream."""
+        return int(self._lib.ruvgnn_ctx_stream(self.handle) or 0)
+
+    def torch_stream(self):
+        """``torch.cuda.ExternalStream`` view of :attr:`stream` (``with torch.cuda.stream(ctx.torch_stream())``)."""
+        import torch
+
+        return torch.cuda.ExternalStream(self.stream, device=torch.device("cuda", self.device))
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.ruvgnn_ctx_launch_count(self.handle))
 
@@ -155,7 +169,7 @@ class RuvectorLayer:
 
     def __init__(self, input_dim: int, hidden_dim: int, heads: int, dropout: float, *,
                  weights: Optional[dict] = None, rng: Optional[np.random.Generator] = None,
-                 ctx: Optional[Context] = None, mode: int = _lib.MODE_FP32_SIMT):
+                 ctx: Optional[Context] = None, mode: Optional[int] = None):
         lib = _lib.load()
         st = lib.ruvgnn_layer_validate(int(input_dim), int(hidden_dim), int(heads), float(dropout))
         if st != 0:
@@ -269,9 +283,15 @@ class RuvectorLayer:
             _lib.check(lib.ruvgnn_layer_create(self.ctx.handle, self.input_dim, self.hidden_dim, self.heads,
                                                self.dropout, C.byref(cw), C.byref(h)))
             self._handle = h
-            if self._mode != _lib.MODE_FP32_SIMT:
+            if self._mode is not None:  # None: the library's default (tensor cores where the shape allows)
                 _lib.check(lib.ruvgnn_layer_set_mode(h, self._mode))
         return self._handle
+
+    @property
+    def mode(self) -> int:
+        """The arithmetic mode the device layer runs in (``MODE_FP32_TC`` by default where the shape
+        allows it, else ``MODE_FP32_SIMT``)."""
+        return int(_lib.load().ruvgnn_layer_mode(self._device_layer()))
 
     def set_mode(self, mode: int):
         self._mode = mode
@@ -323,7 +343,12 @@ class RuvectorLayer:
 
     def forward_graph_device(self, x_ptr: int, out_ptr: int, graph: DeviceGraph, *, asynchronous: bool = True,
                              timing: bool = False):
-        """Batched forward on device pointers (e.g. ``torch.Tensor.data_ptr()``), enqueue only."""
+        """Batched forward on device pointers (e.g. ``torch.Tensor.data_ptr()``), enqueue only.
+
+        Stream contract: the kernels run on ``self.ctx.stream``.  The buffers must have been produced
+        on (or synchronised with) that stream, and readers must wait for it -- create the ctx on the
+        caller's stream (``Context(dev, torch.cuda.current_stream().cuda_stream)``) or work under
+        ``with torch.cuda.stream(ctx.torch_stream())``."""
         flags = _lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.FWD_TIMING if timing else 0)
         _lib.check(_lib.load().ruvgnn_layer_forward(
             self.ctx.handle, self._device_layer(), graph.handle, C.c_void_p(x_ptr), C.c_void_p(out_ptr), flags))

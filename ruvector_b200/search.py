@@ -66,6 +66,6 @@ def hierarchical_forward(query, layer_embeddings: Sequence, gnn_layers: Sequence
     flat = np.empty(q.shape[0] * cap, dtype=F32)
     _lib.check(_lib.load().ruvgnn_hierarchical_forward(
         ctx.handle, q.ctypes.data_as(_fp), q.shape[0], q.shape[1], ptrs, rows, dims, lh, n_levels,
-        flat.ctypes.data_as(_fp), cap, C.byref(od)))
+        flat.ctypes.data_as(_fp), flat.size, C.byref(od)))
     out = flat[: q.shape[0] * od.value].reshape(q.shape[0], od.value).copy()
     return out[0] if single else out

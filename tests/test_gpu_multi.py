@@ -36,7 +36,12 @@ def test_rebuilt_halo_rows_carry_the_owner_bits(built, d, heads, mode):
     from ruvector_b200 import _lib, synth
 
     lib = _lib.load()
-    ctx = rv.Context(0)
+    # the torch tensors below are produced on torch's current stream: the ctx must enqueue on the
+    # same one (a ctx created without a stream owns a non-blocking stream that does not order
+    # against it)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = rv.Context(0, stream.cuda_stream)
     n = 3000
     layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=d), ctx=ctx,
                              mode=rv.MODE_FP32_TC if mode == "tc" else rv.MODE_FP32_SIMT)
@@ -64,3 +69,4 @@ def test_rebuilt_halo_rows_carry_the_owner_bits(built, d, heads, mode):
     _lib.check(lib.ruvgnn_ctx_set_sm_limit(ctx.handle, 0))
     ctx.sync()
     assert np.array_equal(sent.cpu().numpy(), again.cpu().numpy())
+    torch.cuda.set_stream(torch.cuda.default_stream())

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(built):
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert _lib.load().ruvgnn_abi_version() == 1
+    assert _lib.load().ruvgnn_abi_version() == 2
 
 
 def test_constructor_rejects_bad_dropout_with_reference_message(built):  # layer.rs:353-358,536-539
