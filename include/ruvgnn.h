@@ -161,6 +161,7 @@ int32_t ruvgnn_hnsw_dump_level_csr(const ruvgnn_hnsw_dump *d, uint32_t level, ui
  * RUVGNN_GRAPH_PRENORMALIZED: edge_w already holds the normalised weights of
  * layer.rs:426-432 (used by the per-node entry to keep zip truncation). */
 #define RUVGNN_GRAPH_PRENORMALIZED 1u
+#define RUVGNN_GRAPH_DEVICE_PTRS 2u /* row_ptr / col_idx / edge_w are device pointers (copied) */
 int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
                             const uint64_t *row_ptr, const uint32_t *col_idx, const float *edge_w,
                             uint32_t flags, ruvgnn_graph **out);

@@ -56,7 +56,7 @@ SYMBOLS = {
     "ruvgnn_hnsw_dump_info": (C.c_int32, [_vp, _u64p, _u64p, _u32p, _u32p, _u64p, _u32p, _u64p]),
     "ruvgnn_hnsw_dump_level_edges": (C.c_int32, [_vp, C.c_uint32, _u64p]),
     "ruvgnn_hnsw_dump_level_csr": (C.c_int32, [_vp, C.c_uint32, C.c_uint64, _u64p, _u32p, c_float_p]),
-    "ruvgnn_graph_create": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, _u64p, _u32p, c_float_p, C.c_uint32, C.POINTER(_vp)]),
+    "ruvgnn_graph_create": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, C.c_uint32, C.POINTER(_vp)]),
     "ruvgnn_graph_dims": (C.c_int32, [_vp, _u64p, _u64p, _u64p]),
     "ruvgnn_graph_download": (C.c_int32, [_vp, _u64p, _u32p, c_float_p]),
     "ruvgnn_graph_destroy": (None, [_vp]),
@@ -106,7 +106,7 @@ FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
 DIST_EXACT = 16
 PART_DEVICE_PTRS, PART_FORCE_SPARSE, PART_FORCE_DENSE = 1, 2, 4
 NCCL_ID_BYTES = 128
-GRAPH_PRENORMALIZED = 1
+GRAPH_PRENORMALIZED, GRAPH_DEVICE_PTRS = 1, 2
 MODE_FP32_SIMT, MODE_FP32_TC, MODE_TF32 = 0, 1, 2
 
 

@@ -853,22 +853,36 @@ int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
   if (!ctx || !row_ptr) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx / row_ptr is null");
   if (n_cols < n_nodes) return fail(RUVGNN_ERR_INVALID_INPUT, "n_cols < n_nodes");
   if (n_cols > 0xffffffffull) return fail(RUVGNN_ERR_INVALID_INPUT, "n_cols exceeds u32 col_idx");
-  if (row_ptr[0] != 0) return fail(RUVGNN_ERR_INVALID_INPUT, "row_ptr[0] must be 0");
-  const uint64_t n_edges = row_ptr[n_nodes];
-  if (n_edges && (!col_idx || !edge_w))
-    return fail(RUVGNN_ERR_INVALID_INPUT, "col_idx / edge_w is null");
   DeviceGuard dg(ctx->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
+  const bool dev_ptrs = flags & RUVGNN_GRAPH_DEVICE_PTRS;
+  const cudaMemcpyKind kind = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  uint64_t ends[2] = {0, 0};
+  if (dev_ptrs) {
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(&ends[0], row_ptr, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(&ends[1], row_ptr + n_nodes, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RUVGNN_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  } else {
+    ends[0] = row_ptr[0];
+    ends[1] = row_ptr[n_nodes];
+  }
+  if (ends[0] != 0) return fail(RUVGNN_ERR_INVALID_INPUT, "row_ptr[0] must be 0");
+  const uint64_t n_edges = ends[1];
+  if (n_edges && (!col_idx || !edge_w))
+    return fail(RUVGNN_ERR_INVALID_INPUT, "col_idx / edge_w is null");
   std::unique_ptr<ruvgnn_graph> g(new ruvgnn_graph());
   g->device = ctx->device;
   g->n_nodes = n_nodes;
   g->n_cols = n_cols;
   g->n_edges = n_edges;
-  g->flags = flags;
+  g->flags = flags & RUVGNN_GRAPH_PRENORMALIZED;
   auto cleanup = [&]() {
     if (g->row_ptr) cudaFree(g->row_ptr);
     if (g->col_idx) cudaFree(g->col_idx);
     if (g->edge_w) cudaFree(g->edge_w);
+    g->row_ptr = nullptr;
+    g->col_idx = nullptr;
+    g->edge_w = nullptr;
   };
 #define GTRY(expr)                                                                           \
   do {                                                                                       \
@@ -882,13 +896,10 @@ int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
   GTRY(cudaMalloc(&g->row_ptr, (n_nodes + 1) * sizeof(uint64_t)));
   GTRY(cudaMalloc(&g->col_idx, (n_edges + 4) * sizeof(uint32_t)));
   GTRY(cudaMalloc(&g->edge_w, (n_edges + 4) * sizeof(float)));
-  GTRY(cudaMemcpyAsync(g->row_ptr, row_ptr, (n_nodes + 1) * sizeof(uint64_t),
-                       cudaMemcpyHostToDevice, ctx->stream));
+  GTRY(cudaMemcpyAsync(g->row_ptr, row_ptr, (n_nodes + 1) * sizeof(uint64_t), kind, ctx->stream));
   if (n_edges) {
-    GTRY(cudaMemcpyAsync(g->col_idx, col_idx, n_edges * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                         ctx->stream));
-    GTRY(cudaMemcpyAsync(g->edge_w, edge_w, n_edges * sizeof(float), cudaMemcpyHostToDevice,
-                         ctx->stream));
+    GTRY(cudaMemcpyAsync(g->col_idx, col_idx, n_edges * sizeof(uint32_t), kind, ctx->stream));
+    GTRY(cudaMemcpyAsync(g->edge_w, edge_w, n_edges * sizeof(float), kind, ctx->stream));
   }
   // device-side validation: monotone row_ptr, col_idx < n_cols
   GTRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
@@ -1069,6 +1080,7 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
+  const bool timing = flags & RUVGNN_FWD_TIMING;
   c->timing_valid = false;
   c->state_per_node = false;
   int32_t rc;
@@ -1099,8 +1111,19 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
         return rc;
       dst = c->stack_buf[b];
     }
+    if (timing) {  // one timing slot per layer: ruvgnn_ctx_last_timing then reports per-layer averages
+      c->timing_valid = true;
+      begin_timing_slot(c);
+      cudaEventRecord(c->ev[0], c->stream);
+      cudaEventRecord(c->ev[1], c->stream);
+    }
     if ((rc = do_project(c, layers[l], n, cur))) return rc;
+    if (timing) cudaEventRecord(c->ev[2], c->stream);
     if ((rc = do_aggregate_update(c, layers[l], graphs[l], nullptr, 0, n, dst))) return rc;
+    if (timing) {
+      cudaEventRecord(c->ev[4], c->stream);
+      cudaEventRecord(c->ev[5], c->stream);
+    }
     cur = dst;
   }
   if (!dev_ptrs)

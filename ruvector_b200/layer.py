@@ -94,26 +94,34 @@ class DeviceGraph:
     def __init__(self, ctx: Context, row_ptr, col_idx, edge_w, n_cols: Optional[int] = None, flags: int = 0):
         self._lib = _lib.load()
         self.ctx = ctx
-        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
-        col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
-        edge_w = np.ascontiguousarray(edge_w, dtype=F32)
-        if row_ptr.ndim != 1 or row_ptr.size < 1:
-            raise InvalidInput("row_ptr must be a 1-d array of n_nodes + 1 entries")
-        n = row_ptr.size - 1
-        if col_idx.size != edge_w.size or int(row_ptr[-1]) != col_idx.size:
-            raise InvalidInput("row_ptr[-1], len(col_idx) and len(edge_w) must agree")
         h = C.c_void_p()
-        _lib.check(
-            self._lib.ruvgnn_graph_create(
-                ctx.handle, n, n if n_cols is None else n_cols,
-                row_ptr.ctypes.data_as(C.POINTER(C.c_uint64)),
-                col_idx.ctypes.data_as(C.POINTER(C.c_uint32)), _ptr(edge_w), flags, C.byref(h),
-            )
-        )
+        if hasattr(row_ptr, "data_ptr"):
+            # device tensors (torch): row_ptr int64/uint64 [n+1], col_idx int32/uint32 [E], edge_w float32 [E],
+            # contiguous, produced on (or synchronised with) the ctx stream; the library copies them
+            n, n_edges = int(row_ptr.numel()) - 1, int(col_idx.numel())
+            if row_ptr.element_size() != 8 or col_idx.element_size() != 4 or edge_w.element_size() != 4:
+                raise InvalidInput("device CSR needs 64-bit row_ptr, 32-bit col_idx and float32 edge_w")
+            if int(edge_w.numel()) != n_edges or not (row_ptr.is_contiguous() and col_idx.is_contiguous() and edge_w.is_contiguous()):
+                raise InvalidInput("len(col_idx) and len(edge_w) must agree and the tensors be contiguous")
+            _lib.check(self._lib.ruvgnn_graph_create(
+                ctx.handle, n, n if n_cols is None else n_cols, C.c_void_p(row_ptr.data_ptr()),
+                C.c_void_p(col_idx.data_ptr()), C.c_void_p(edge_w.data_ptr()), flags | _lib.GRAPH_DEVICE_PTRS, C.byref(h)))
+        else:
+            row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+            col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
+            edge_w = np.ascontiguousarray(edge_w, dtype=F32)
+            if row_ptr.ndim != 1 or row_ptr.size < 1:
+                raise InvalidInput("row_ptr must be a 1-d array of n_nodes + 1 entries")
+            n, n_edges = row_ptr.size - 1, int(col_idx.size)
+            if col_idx.size != edge_w.size or int(row_ptr[-1]) != col_idx.size:
+                raise InvalidInput("row_ptr[-1], len(col_idx) and len(edge_w) must agree")
+            _lib.check(self._lib.ruvgnn_graph_create(
+                ctx.handle, n, n if n_cols is None else n_cols, C.c_void_p(row_ptr.ctypes.data),
+                C.c_void_p(col_idx.ctypes.data), C.c_void_p(edge_w.ctypes.data), flags, C.byref(h)))
         self.handle = h
         self.n_nodes = n
         self.n_cols = n if n_cols is None else n_cols
-        self.n_edges = int(col_idx.size)
+        self.n_edges = n_edges
 
     def download(self):
         rp = np.empty(self.n_nodes + 1, dtype=np.uint64)
@@ -352,6 +360,19 @@ class RuvectorLayer:
         flags = _lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.FWD_TIMING if timing else 0)
         _lib.check(_lib.load().ruvgnn_layer_forward(
             self.ctx.handle, self._device_layer(), graph.handle, C.c_void_p(x_ptr), C.c_void_p(out_ptr), flags))
+
+
+def forward_stack_device(layers: Sequence[RuvectorLayer], x_ptr: int, out_ptr: int, graphs: Sequence[DeviceGraph],
+                         asynchronous: bool = True, timing: bool = False):
+    """Stacked forward on device pointers (``ruvgnn_stack_forward``), enqueue only by default; same stream
+    contract as :meth:`RuvectorLayer.forward_graph_device`.  ``timing``: one timing slot per layer."""
+    if len(layers) != len(graphs) or not layers:
+        raise InvalidInput("one graph per layer is required")
+    n = len(layers)
+    lh = (C.c_void_p * n)(*[l._device_layer() for l in layers])
+    gh = (C.c_void_p * n)(*[g.handle for g in graphs])
+    flags = _lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.FWD_TIMING if timing else 0)
+    _lib.check(_lib.load().ruvgnn_stack_forward(layers[0].ctx.handle, lh, gh, n, C.c_void_p(x_ptr), C.c_void_p(out_ptr), flags))
 
 
 def forward_stack(layers: Sequence[RuvectorLayer], x, graphs: Sequence[DeviceGraph], out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -23,6 +23,30 @@ def _p(a):
     return a.ctypes.data_as(c_float_p)
 
 
+class HostLayer:
+    """Host-only stand-in for ruvector_b200.RuvectorLayer (dims + weights, nothing else): lets
+    bench.py's --impl reference arm feed the oracle without ever loading libruvgnn.so."""
+
+    def __init__(self, input_dim, hidden_dim, heads, dropout, weights):
+        self.input_dim, self.hidden_dim, self.heads = int(input_dim), int(hidden_dim), int(heads)
+        self.dropout = float(np.float32(dropout))
+        self.weights = {k: ((np.ascontiguousarray(v[0], dtype=F32), np.ascontiguousarray(v[1], dtype=F32))
+                            if isinstance(v, tuple) else v) for k, v in weights.items()}
+        self.weights["gamma"] = np.ascontiguousarray(weights["gamma"], dtype=F32)
+        self.weights["beta"] = np.ascontiguousarray(weights["beta"], dtype=F32)
+
+    def c_weights(self) -> Weights:
+        from ruvector_b200._lib import LINEAR_NAMES, Linear
+
+        cw = Weights()
+        for name in LINEAR_NAMES:
+            W, b = self.weights[name]
+            setattr(cw, name, Linear(_p(W), _p(b)))
+        cw.gamma, cw.beta = _p(self.weights["gamma"]), _p(self.weights["beta"])
+        cw.eps = float(self.weights.get("eps", 1e-5))
+        return cw
+
+
 class Oracle:
     def __init__(self):
         path = ROOT / "oracle" / "liboracle.so"
