@@ -138,6 +138,23 @@ int32_t ruvgnn_pack_neighbours(uint64_t n_nodes, const void *const *lists, const
                                size_t stride, size_t id_offset, size_t dist_offset,
                                uint64_t *row_ptr, uint32_t *col_idx, float *edge_w);
 
+/* Union-of-levels adjacency, the CSR analogue of hnsw_rs flatten_point
+ * (patches/hnsw_rs/src/flatten.rs:74-89): per node the lists of all n_levels level CSRs are
+ * concatenated (level 0 first) and sorted by ascending distance (stable; the reference's
+ * sort_unstable leaves equal distances unordered), duplicates kept.  NaN distance ->
+ * RUVGNN_ERR_INVALID_INPUT (the reference panics).  row_ptr: [n_nodes+1]; col_idx / edge_w:
+ * [sum of the levels' edges].  Host only. */
+int32_t ruvgnn_flatten_levels(uint64_t n_nodes, uint32_t n_levels, const uint64_t *const *row_ptrs,
+                              const uint32_t *const *col_idxs, const float *const *edge_ws,
+                              uint64_t *row_ptr, uint32_t *col_idx, float *edge_w);
+
+/* BFS vertex order for locality before range partitioning: DataLoader::reorder_bfs
+ * (crates/ruvector-gnn/src/cold_tier.rs:307-342) with the CSR in stored order as the edge list
+ * (u = row, v = column; every edge joins both endpoints' lists).  order[p] = the node that moves
+ * to position p.  O(n_nodes + n_edges).  Host only. */
+int32_t ruvgnn_bfs_order(uint64_t n_nodes, const uint64_t *row_ptr, const uint32_t *col_idx,
+                         uint64_t *order);
+
 /* Reads an hnsw_rs graph dump (`<basename>.hnsw.graph`, written by Hnsw::file_dump:
  * Description patches/hnsw_rs/src/hnswio.rs:878-918, PointIndexation :1303-1340,
  * dump_point :1063-1096; Full and Light modes, description versions 2-4) and exposes each
@@ -268,6 +285,33 @@ int32_t ruvgnn_layer_expand_halo(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
 int32_t ruvgnn_layer_aggregate_update(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
                                       const ruvgnn_graph *graph, const float *halo_dev,
                                       uint64_t row_begin, uint64_t row_end, float *out_dev);
+
+/* ---- embedding store files as X source / output sink ----------------------------
+ * A store is a file of f32 rows at a fixed stride.  The two on-disk layouts of the reference are
+ * used in place: MmapManager's headerless dense [max_nodes][d_embed] file
+ * (crates/ruvector-gnn/src/mmap.rs:118-186, node i at byte i * d_embed * 4, :199-203) and the
+ * cold tier's FeatureStorage (crates/ruvector-gnn/src/cold_tier.rs:17-18,45-75: 24-byte
+ * little-endian header dim | num_nodes | block_size, then one page-aligned block per node). */
+typedef struct {
+  const char *path;          /* the caller keeps the string alive for the duration of the call */
+  uint64_t offset_bytes;     /* first row: 0 (MmapManager) or 24 (FeatureStorage) */
+  uint64_t row_stride_bytes; /* d_embed * 4, or the FeatureStorage block_size */
+  uint32_t dim;              /* floats per row */
+  uint64_t rows;             /* rows the file holds */
+} ruvgnn_store;
+/* MmapManager::new(path, d_embed, max_nodes) view of an existing file (size checked). */
+int32_t ruvgnn_store_describe_mmap(const char *path, uint32_t d_embed, uint64_t max_nodes,
+                                   ruvgnn_store *out);
+/* FeatureStorage::open(path): reads and validates the header. */
+int32_t ruvgnn_store_describe_feature_storage(const char *path, ruvgnn_store *out);
+/* The batched forward of ruvgnn_layer_forward with X streamed from x_store and the new embeddings
+ * streamed into out_store (distinct files; rows [0, graph n_nodes) of each): rows move file ->
+ * pinned block -> device block -> projection and back in blocks of block_rows rows (0: 131072),
+ * double-buffered, so neither X nor the output is resident as a whole on the host or in HBM.
+ * Results are the bits of ruvgnn_layer_forward on the same rows. */
+int32_t ruvgnn_layer_forward_store(ruvgnn_ctx *ctx, const ruvgnn_layer *layer,
+                                   const ruvgnn_graph *graph, const ruvgnn_store *x_store,
+                                   const ruvgnn_store *out_store, uint64_t block_rows);
 
 /* Diagnostic form of the multi-pass gather the partitioned forward uses (below): the layer
  * forward over a single-device graph with the neighbour list of every node processed in

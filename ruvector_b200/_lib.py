@@ -51,6 +51,8 @@ SYMBOLS = {
     "ruvgnn_layer_mode": (C.c_uint32, [_vp]),
     "ruvgnn_layer_destroy": (None, [_vp]),
     "ruvgnn_pack_neighbours": (C.c_int32, [C.c_uint64, C.POINTER(_vp), _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u32p, c_float_p]),
+    "ruvgnn_flatten_levels": (C.c_int32, [C.c_uint64, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _u64p, _u32p, c_float_p]),
+    "ruvgnn_bfs_order": (C.c_int32, [C.c_uint64, _u64p, _u32p, _u64p]),
     "ruvgnn_hnsw_dump_open": (C.c_int32, [C.c_char_p, C.POINTER(_vp)]),
     "ruvgnn_hnsw_dump_close": (None, [_vp]),
     "ruvgnn_hnsw_dump_info": (C.c_int32, [_vp, _u64p, _u64p, _u32p, _u32p, _u64p, _u32p, _u64p]),
@@ -72,6 +74,9 @@ SYMBOLS = {
     "ruvgnn_layer_messages": (C.c_int32, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "ruvgnn_layer_expand_halo": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_aggregate_update": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
+    "ruvgnn_store_describe_mmap": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint64, _vp]),
+    "ruvgnn_store_describe_feature_storage": (C.c_int32, [C.c_char_p, _vp]),
+    "ruvgnn_layer_forward_store": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_uint64]),
     "ruvgnn_layer_forward_split": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _u64p, C.c_uint32]),
     "ruvgnn_dist_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
     "ruvgnn_dist_create": (C.c_int32, [_vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.POINTER(_vp)]),
@@ -86,6 +91,13 @@ SYMBOLS = {
     "ruvgnn_dist_forward": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32]),
     "ruvgnn_dist_last_stats": (C.c_int32, [_vp, _vp]),
 }
+
+
+class Store(C.Structure):
+    """ruvgnn_store (include/ruvgnn.h)."""
+
+    _fields_ = [("path", C.c_char_p), ("offset_bytes", C.c_uint64), ("row_stride_bytes", C.c_uint64),
+                ("dim", C.c_uint32), ("rows", C.c_uint64)]
 
 
 class PartitionInfo(C.Structure):

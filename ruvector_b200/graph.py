@@ -52,15 +52,59 @@ class CsrGraph:
         return DeviceGraph(ctx or default_context(0), self.row_ptr, self.col_idx, self.edge_w, n_cols, flags)
 
 
-def locality_order(g: CsrGraph) -> np.ndarray:
-    """A node order that pulls neighbours together (reverse Cuthill-McKee on the symmetrised
-    adjacency): ``perm[p]`` = the node that moves to position ``p``.
+def bfs_order(g: CsrGraph) -> np.ndarray:
+    """The reference's own locality reorder, ``DataLoader::reorder_bfs``
+    (crates/ruvector-gnn/src/cold_tier.rs:307-342), over the CSR in stored order
+    (``ruvgnn_bfs_order``, native, O(N + E)): ``perm[p]`` = the node that moves to position ``p``."""
+    lib = _lib.load()
+    n = g.n_nodes
+    rp = np.ascontiguousarray(g.row_ptr, dtype=np.uint64)
+    ci = np.ascontiguousarray(g.col_idx, dtype=np.uint32)
+    order = np.empty(n, dtype=np.uint64)
+    _lib.check(lib.ruvgnn_bfs_order(n, rp.ctypes.data_as(C.POINTER(C.c_uint64)), ci.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                    order.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return order.astype(np.int64)
+
+
+def flatten_levels(levels: Sequence[CsrGraph]) -> CsrGraph:
+    """Union-of-levels adjacency sorted by distance, the CSR analogue of hnsw_rs ``flatten_point``
+    (patches/hnsw_rs/src/flatten.rs:74-89); ``levels[l]`` is the CSR of HNSW level ``l`` over the same nodes."""
+    lib = _lib.load()
+    if not levels:
+        raise InvalidInput("at least one level is required")
+    n = levels[0].n_nodes
+    if any(l.n_nodes != n for l in levels):
+        raise InvalidInput("every level must cover the same nodes")
+    rps = [np.ascontiguousarray(l.row_ptr, dtype=np.uint64) for l in levels]
+    cis = [np.ascontiguousarray(l.col_idx, dtype=np.uint32) for l in levels]
+    ews = [np.ascontiguousarray(l.edge_w, dtype=np.float32) for l in levels]
+    k = len(levels)
+    total = sum(int(c.size) for c in cis)
+    vp = C.c_void_p * k
+    row_ptr = np.empty(n + 1, dtype=np.uint64)
+    col_idx = np.empty(total, dtype=np.uint32)
+    edge_w = np.empty(total, dtype=np.float32)
+    _lib.check(lib.ruvgnn_flatten_levels(
+        n, k, vp(*[a.ctypes.data for a in rps]), vp(*[a.ctypes.data for a in cis]), vp(*[a.ctypes.data for a in ews]),
+        row_ptr.ctypes.data_as(C.POINTER(C.c_uint64)), col_idx.ctypes.data_as(C.POINTER(C.c_uint32)),
+        edge_w.ctypes.data_as(_lib.c_float_p)))
+    return CsrGraph(row_ptr, col_idx, edge_w)
+
+
+def locality_order(g: CsrGraph, method: str = "bfs") -> np.ndarray:
+    """A node order that pulls neighbours together: ``perm[p]`` = the node that moves to position ``p``.
+    ``method="bfs"`` (default): :func:`bfs_order`, the reference's reorder, native and O(N + E);
+    ``method="rcm"``: reverse Cuthill-McKee on the symmetrised adjacency (SciPy, small graphs only).
 
     HNSW ids are insertion order, so a contiguous id range is a random node sample and nearly
     every neighbour of a range partition is remote.  After this order most neighbours of a range
     are inside it ("optional locality permutation applied identically to X, CSR rows
     and col_idx; ... inverted on output").  Apply with :func:`permute_graph`, ``x[perm]`` and
     ``out[inverse_permutation(perm)]``."""
+    if method == "bfs":
+        return bfs_order(g)
+    if method != "rcm":
+        raise InvalidInput("method must be 'bfs' or 'rcm'")
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import reverse_cuthill_mckee
 

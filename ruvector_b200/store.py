@@ -9,8 +9,15 @@ Two on-disk layouts of the reference are mapped without conversion:
   page-aligned block of ``block_size`` bytes per node, the first ``dim * 4`` of which hold
   the features (:120-149).
 
-Host-side byte work only: the arrays returned are ``numpy.memmap`` views handed to
-``RuvectorLayer.forward_graph`` (which does the H2D/D2H); nothing here computes the layer.
+Two ways to run the layer on a store:
+
+* :func:`forward_store_files` -- the product path: ``ruvgnn_layer_forward_store`` streams the rows
+  file -> pinned block -> device block -> projection and the new embeddings back to the output
+  file, double-buffered, so neither X nor the output is ever resident as a whole (host or HBM);
+* :func:`forward_from_store` -- convenience for small stores: ``numpy.memmap`` views handed to
+  ``RuvectorLayer.forward_graph``.
+
+Host-side byte work only; nothing here computes the layer.
 """
 from __future__ import annotations
 
@@ -72,6 +79,42 @@ def open_feature_storage(path, mode: str = "r") -> np.ndarray:
     raw = np.memmap(path, dtype=np.uint8, mode=mode, offset=HEADER_SIZE, shape=(num_nodes * block,))
     rows = raw.view(np.float32).reshape(num_nodes, block // 4)
     return rows[:, :dim]
+
+
+def describe_mmap(path, d_embed: int, max_nodes: int):
+    """``ruvgnn_store`` descriptor of a ``MmapManager`` file (size checked by the library)."""
+    import ctypes as C
+
+    from . import _lib
+
+    st = _lib.Store()
+    st._path = os.fsencode(str(path))
+    _lib.check(_lib.load().ruvgnn_store_describe_mmap(st._path, int(d_embed), int(max_nodes), C.byref(st)))
+    return st
+
+
+def describe_feature_storage(path):
+    """``ruvgnn_store`` descriptor of a cold-tier ``FeatureStorage`` file (header read by the library)."""
+    import ctypes as C
+
+    from . import _lib
+
+    st = _lib.Store()
+    st._path = os.fsencode(str(path))
+    _lib.check(_lib.load().ruvgnn_store_describe_feature_storage(st._path, C.byref(st)))
+    return st
+
+
+def forward_store_files(layer, graph, x_store, out_store, block_rows: int = 0):
+    """``ruvgnn_layer_forward_store``: X streamed from ``x_store``, the new embeddings streamed into
+    ``out_store`` (descriptors from :func:`describe_mmap` / :func:`describe_feature_storage`; distinct
+    files).  Blocks until the output file holds the result."""
+    import ctypes as C
+
+    from . import _lib
+
+    _lib.check(_lib.load().ruvgnn_layer_forward_store(layer.ctx.handle, layer._device_layer(), graph.handle,
+                                                      C.byref(x_store), C.byref(out_store), int(block_rows)))
 
 
 def forward_from_store(layer, x_store: np.ndarray, graph, out_store: np.ndarray | None = None) -> np.ndarray:

@@ -231,3 +231,79 @@ def test_header_is_plain_c_and_cxx(tmp_path):
     hpp.write_text('#include "ruvgnn.hpp"\nint main() { return 0; }\n')
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", str(root / "include"), str(hpp)],
                    check=True)
+
+
+def _reorder_bfs_reference(adjacency, num_nodes):
+    """Python restatement of DataLoader::reorder_bfs (crates/ruvector-gnn/src/cold_tier.rs:307-342)."""
+    from collections import deque
+
+    adj = [[] for _ in range(num_nodes)]
+    for u, v in adjacency:
+        if u < num_nodes and v < num_nodes:
+            adj[u].append(v)
+            adj[v].append(u)
+    visited, order, queue = [False] * num_nodes, [], deque()
+    for start in range(num_nodes):
+        if visited[start]:
+            continue
+        visited[start] = True
+        queue.append(start)
+        while queue:
+            node = queue.popleft()
+            order.append(node)
+            for nb in adj[node]:
+                if not visited[nb]:
+                    visited[nb] = True
+                    queue.append(nb)
+    return order
+
+
+@pytest.mark.parametrize("seed,loc", [(1, 0.0), (2, 0.7), (3, 1.0)])
+def test_bfs_order_is_the_references_reorder_bfs(built, seed, loc):
+    """ruvgnn_bfs_order against the restated reference on the CSR's edge list (stored order), incl.
+    isolated nodes, several components and a self loop; and it is the scalable default of
+    locality_order (the SciPy RCM stays selectable)."""
+    from ruvector_b200.graph import CsrGraph, bfs_order, locality_order, permute_graph, remote_edge_fraction
+
+    n = 3000
+    g = synth.hnsw_like_graph(n, 6, seed=seed, locality=loc, window=25, iso_frac=0.2)
+    col = g.col_idx.copy()
+    if col.size:
+        col[int(g.row_ptr[5])] = 5 if g.row_ptr[6] > g.row_ptr[5] else col[int(g.row_ptr[5])]  # a self loop
+    g = CsrGraph(g.row_ptr, col, g.edge_w)
+    rows = np.repeat(np.arange(n), g.degrees())
+    want = _reorder_bfs_reference(list(zip(rows.tolist(), g.col_idx.tolist())), n)
+    got = bfs_order(g)
+    assert got.tolist() == want
+    assert np.array_equal(locality_order(g), got)
+    assert np.array_equal(np.sort(locality_order(g, method="rcm")), np.arange(n))
+    if loc == 1.0:  # a shuffled window graph: BFS pulls the neighbours back together
+        rng = np.random.default_rng(seed)
+        hidden = permute_graph(synth.hnsw_like_graph(20000, 8, seed=9, locality=1.0, window=40, iso_frac=0.0), rng.permutation(20000))
+        assert remote_edge_fraction(hidden, 8) > 0.8
+        assert remote_edge_fraction(permute_graph(hidden, bfs_order(hidden)), 8) < 0.25
+    assert bfs_order(CsrGraph(np.zeros(1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.float32))).size == 0
+
+
+def test_flatten_levels_mirrors_flatten_point(built):
+    """Union-of-levels CSR = hnsw_rs flatten_point (patches/hnsw_rs/src/flatten.rs:74-89): per node the
+    concatenation of all level lists sorted by distance (stable), duplicates kept; NaN is an error."""
+    from ruvector_b200.graph import CsrGraph, flatten_levels
+
+    n = 500
+    levels = [synth.hnsw_like_graph(n, 8, seed=4, level=l, iso_frac=0.05) for l in range(3)]
+    flat = flatten_levels(levels)
+    assert flat.n_edges == sum(l.n_edges for l in levels)
+    for i in range(n):
+        recs = []
+        for l in levels:
+            s, e = int(l.row_ptr[i]), int(l.row_ptr[i + 1])
+            recs += list(zip(l.edge_w[s:e].tolist(), l.col_idx[s:e].tolist()))
+        recs.sort(key=lambda r: r[0])  # Python's sort is stable, like the native one
+        s, e = int(flat.row_ptr[i]), int(flat.row_ptr[i + 1])
+        assert flat.edge_w[s:e].tolist() == [r[0] for r in recs]
+        assert flat.col_idx[s:e].tolist() == [r[1] for r in recs]
+    assert np.array_equal(flatten_levels(levels[:1]).col_idx, levels[0].col_idx)  # level 0 alone is already sorted
+    bad = CsrGraph(np.array([0, 1], np.uint64), np.array([0], np.uint32), np.array([np.nan], np.float32))
+    with pytest.raises(rv.InvalidInput):
+        flatten_levels([bad])
