@@ -179,6 +179,11 @@ int32_t ruvgnn_hnsw_dump_level_csr(const ruvgnn_hnsw_dump *d, uint32_t level, ui
  * layer.rs:426-432 (used by the per-node entry to keep zip truncation). */
 #define RUVGNN_GRAPH_PRENORMALIZED 1u
 #define RUVGNN_GRAPH_DEVICE_PTRS 2u /* row_ptr / col_idx / edge_w are device pointers (copied) */
+/* A graph in which fewer than half of the rows have neighbours (upper HNSW levels: ~n / M^l nodes
+ * own a list) also gets the list of those rows; the forward then runs Q projection, gather and
+ * update on them alone and LN(W_msg x + b) (layer.rs:385-389) on the rest -- same bits, far less
+ * work.  RUVGNN_GRAPH_NO_ACTIVE_LIST keeps the dense path (tests compare the two). */
+#define RUVGNN_GRAPH_NO_ACTIVE_LIST 4u
 int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
                             const uint64_t *row_ptr, const uint32_t *col_idx, const float *edge_w,
                             uint32_t flags, ruvgnn_graph **out);

@@ -118,7 +118,7 @@ FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
 DIST_EXACT = 16
 PART_DEVICE_PTRS, PART_FORCE_SPARSE, PART_FORCE_DENSE = 1, 2, 4
 NCCL_ID_BYTES = 128
-GRAPH_PRENORMALIZED, GRAPH_DEVICE_PTRS = 1, 2
+GRAPH_PRENORMALIZED, GRAPH_DEVICE_PTRS, GRAPH_NO_ACTIVE_LIST = 1, 2, 4
 MODE_FP32_SIMT, MODE_FP32_TC, MODE_TF32 = 0, 1, 2
 
 

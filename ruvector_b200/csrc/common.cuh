@@ -146,6 +146,7 @@ struct LayerNormArgs {
   float *out = nullptr;  // [rows][H] logical order
   uint64_t row_begin = 0, row_end = 0;
   uint32_t H = 0, P = 0;
+  const uint32_t *scatter = nullptr;  // row r is written to out[scatter[r]] (compacted active rows)
 };
 cudaError_t launch_layernorm(const LayerNormArgs &a, cudaStream_t s, uint64_t *launches);
 cudaError_t launch_pack_rows(const float *src, int64_t ld_src, uint32_t row_floats,

@@ -88,6 +88,12 @@ struct ruvgnn_graph {
   uint32_t *col_idx = nullptr;
   float *edge_w = nullptr;
   bool owns = true;  // false: the arrays belong to someone else (ruvgnn_partition)
+  // Sparse levels (upper HNSW levels: ~n / M^l nodes have a list): the rows with at least one
+  // neighbour, and the CSR offsets of just those rows.  Set only when fewer than half of the rows
+  // are active; the forward then runs Q projection, gather and update on the active rows alone.
+  uint64_t n_active = 0;
+  uint32_t *active_idx = nullptr;   // [n_active] ascending node ids
+  uint64_t *row_ptr_active = nullptr;  // [n_active + 1]
 };
 
 namespace ruvgnn {
@@ -149,6 +155,12 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
 // K-upd over rows [rb, re) of at most upd_block() rows (the gather's final pass has run).
 int32_t update_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, uint64_t rb,
                     uint64_t re, float *out_dev);
+// Whole layer on device buffers: project -> gather -> update, with the sparse-level form (only the
+// rows that have neighbours go through Q projection, gather and update; the others are
+// LN(W_msg x + b), layer.rs:385-389) when the graph carries an active-row list and the layer runs
+// the single-row gather.  Records the per-stage timing events when `timing`.
+int32_t forward_device(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, const float *x_dev,
+                       float *out_dev, bool timing);
 // K-agg (single pass, or `pass` as the final pass) + K-upd, block by block.
 int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
                             const float *halo, uint64_t rb, uint64_t re, float *out_dev,

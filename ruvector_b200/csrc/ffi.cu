@@ -309,86 +309,194 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
 }
 
 // K-upd over rows [rb, re), re - rb <= upd_block(): out-proj + combine + W_agg, GRU, dropout
-// scale, LayerNorm (layer.rs:156-159,407-417).
-int32_t update_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, uint64_t rb,
-                    uint64_t re, float *out_dev) {
+// scale, LayerNorm (layer.rs:156-159,407-417).  All bases are indexed by the row number (already
+// shifted by the caller); `scatter` sends row r's output to out[scatter[r]].
+struct UpdIO {
+  const float *oa = nullptr;  // R = 3: o | agg [row][2H];  R = 1: S_0..S_{h-1} | agg [row][(h+1)H]
+  const float *m = nullptr;   // message rows (GRU hidden state)
+  int64_t ldm = 0;
+  float *T0 = nullptr, *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;  // [row][H]
+  const uint64_t *row_ptr = nullptr;  // LayerNorm row select (deg == 0 -> LN(m)); nullptr: every row updated
+  const uint32_t *scatter = nullptr;
+  float *out = nullptr;
+};
+static int32_t update_rows_io(ruvgnn_ctx *c, const ruvgnn_layer *L, const UpdIO &io, uint64_t rb,
+                              uint64_t re) {
   const uint32_t H = L->H;
-  const uint64_t n = c->proj_rows;
-  Ws w = carve(c, L, n);
-  // T0..T3 hold rows [rb, re) only (row r at index r - rb); OA / SA likewise unless the gather
-  // state is kept per node.  The GEMM arguments below index them by the node's row, so shift
-  // the bases once.
-  const uint64_t sb = c->state_per_node ? 0 : rb;
-  w.OA -= (ptrdiff_t)(sb * 2 * H);
-  if (L->r1) w.SA -= (ptrdiff_t)(sb * (uint64_t)(L->heads + 1) * H);
-  w.T0 -= (ptrdiff_t)(rb * H);
-  w.T1 -= (ptrdiff_t)(rb * H);
-  w.T2 -= (ptrdiff_t)(rb * H);
-  w.T3 -= (ptrdiff_t)(rb * H);
   const int64_t rows = (int64_t)(re - rb);
-  const float *m = w.m + rb * w.ldm;
+  const float *m = io.m + rb * io.ldm;
   int32_t rc;
   if (!L->r1) {  // combined = W_o o + b_o + agg
     GemmArgs g;
     g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H;
-    g.A1 = w.OA + rb * 2 * H; g.lda1 = 2 * H;
+    g.A1 = io.oa + rb * 2 * H; g.lda1 = 2 * H;
     g.W = L->Wo; g.bias = L->bo;
-    g.add = w.OA + rb * 2 * H + H; g.ldadd = 2 * H;
-    g.out = w.T0 + rb * H; g.ldo = H;
+    g.add = io.oa + rb * 2 * H + H; g.ldadd = 2 * H;
+    g.out = io.T0 + rb * H; g.ldo = H;
     if ((rc = run_gemm(c, L, g, EPI_BIAS_ADD, TC_W_O))) return rc;
   } else {  // combined = sum_g (W_o[:,g] W_v[g]) S_g + (W_o b_v + b_o) + agg
     const int64_t ld = (int64_t)(L->heads + 1) * H;
     GemmArgs g;
     g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)(L->heads * H);
-    g.A1 = w.SA + rb * ld; g.lda1 = ld;
+    g.A1 = io.oa + rb * ld; g.lda1 = ld;
     g.W = L->Wov; g.bias = L->bov;
-    g.add = w.SA + rb * ld + (size_t)L->heads * H; g.ldadd = ld;
-    g.out = w.T0 + rb * H; g.ldo = H;
+    g.add = io.oa + rb * ld + (size_t)L->heads * H; g.ldadd = ld;
+    g.out = io.T0 + rb * H; g.ldo = H;
     if ((rc = run_gemm(c, L, g, EPI_BIAS_ADD, TC_W_O))) return rc;
   }
   {  // a = W_agg combined + b_agg
     GemmArgs g;
     g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H;
-    g.A1 = w.T0 + rb * H; g.lda1 = H;
+    g.A1 = io.T0 + rb * H; g.lda1 = H;
     g.W = L->Wagg; g.bias = L->bagg;
-    g.out = w.T1 + rb * H; g.ldo = H;
+    g.out = io.T1 + rb * H; g.ldo = H;
     if ((rc = run_gemm(c, L, g, EPI_BIAS, TC_W_AGG))) return rc;
   }
   {  // z = sigma(W_z a + U_z m + b), rh = sigma(W_r a + U_r m + b) * m
     GemmArgs g;
     g.M = rows; g.N = (int32_t)(2 * H); g.K1 = (int32_t)H; g.K2 = (int32_t)H;
-    g.A1 = w.T1 + rb * H; g.lda1 = H;
-    g.A2 = m; g.lda2 = w.ldm;
+    g.A1 = io.T1 + rb * H; g.lda1 = H;
+    g.A2 = m; g.lda2 = io.ldm;
     g.W = L->Wzr; g.bias = L->bzr;
-    g.m = m; g.ldm = w.ldm;
-    g.z = w.T2 + rb * H; g.ldz = H;
-    g.rh = w.T3 + rb * H; g.ldrh = H;
+    g.m = m; g.ldm = io.ldm;
+    g.z = io.T2 + rb * H; g.ldz = H;
+    g.rh = io.T3 + rb * H; g.ldrh = H;
     g.H = (int32_t)H;
     if ((rc = run_gemm(c, L, g, EPI_GATES, TC_W_ZR))) return rc;
   }
   {  // d = ((1-z) m + z tanh(W_h a + U_h rh + b)) * (1-p)
     GemmArgs g;
     g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H; g.K2 = (int32_t)H;
-    g.A1 = w.T1 + rb * H; g.lda1 = H;
-    g.A2 = w.T3 + rb * H; g.lda2 = H;
+    g.A1 = io.T1 + rb * H; g.lda1 = H;
+    g.A2 = io.T3 + rb * H; g.lda2 = H;
     g.W = L->Wh; g.bias = L->bh;
-    g.m = m; g.ldm = w.ldm;
-    g.z = w.T2 + rb * H; g.ldz = H;
-    g.out = w.T0 + rb * H; g.ldo = H;
+    g.m = m; g.ldm = io.ldm;
+    g.z = io.T2 + rb * H; g.ldz = H;
+    g.out = io.T0 + rb * H; g.ldo = H;
     g.H = (int32_t)H;
     g.keep = 1.0f - L->host.dropout;
     if ((rc = run_gemm(c, L, g, EPI_GRU, TC_W_H))) return rc;
   }
   LayerNormArgs ln;
-  ln.d = w.T0; ln.ldd = H;
-  ln.m = w.m; ln.ldm = w.ldm;
-  ln.row_ptr = G->row_ptr;
+  ln.d = io.T0; ln.ldd = H;
+  ln.m = io.m; ln.ldm = io.ldm;
+  ln.row_ptr = io.row_ptr;
   ln.gamma = L->gamma; ln.beta = L->beta; ln.eps = L->host.eps;
-  ln.out = out_dev;
+  ln.out = io.out;
+  ln.scatter = io.scatter;
   ln.row_begin = rb; ln.row_end = re;
   ln.H = H; ln.P = L->ord.P;
   RUVGNN_CUDA_TRY(launch_layernorm(ln, c->stream, &c->launches));
   return RUVGNN_OK;
+}
+
+int32_t update_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, uint64_t rb,
+                    uint64_t re, float *out_dev) {
+  const uint32_t H = L->H;
+  Ws w = carve(c, L, c->proj_rows);
+  // T0..T3 hold rows [rb, re) only (row r at index r - rb); OA / SA likewise unless the gather
+  // state is kept per node.
+  const uint64_t sb = c->state_per_node ? 0 : rb;
+  UpdIO io;
+  io.oa = L->r1 ? w.SA - (ptrdiff_t)(sb * (uint64_t)(L->heads + 1) * H) : w.OA - (ptrdiff_t)(sb * 2 * H);
+  io.m = w.m;
+  io.ldm = w.ldm;
+  io.T0 = w.T0 - (ptrdiff_t)(rb * H);
+  io.T1 = w.T1 - (ptrdiff_t)(rb * H);
+  io.T2 = w.T2 - (ptrdiff_t)(rb * H);
+  io.T3 = w.T3 - (ptrdiff_t)(rb * H);
+  io.row_ptr = G->row_ptr;
+  io.out = out_dev;
+  return update_rows_io(c, L, io, rb, re);
+}
+
+// Sparse level (R = 1 layers): M = W_msg X + b for every row; out = LN(M) for every row (the
+// no-neighbour path, layer.rs:385-389); then only the active rows -- compacted -- go through the
+// folded-query GEMM, the gather and the update, and their LayerNorm rows are scattered over the
+// LN(M) rows.  Each row sees exactly the arithmetic of the dense path (a GEMM output row depends on
+// its own input row only), so the results are bit-identical to it.
+static int32_t forward_sparse_level(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
+                                    const float *x_dev, float *out_dev, bool timing) {
+  const uint32_t H = L->H, h = L->heads;
+  const uint64_t n = G->n_nodes, na = G->n_active;
+  int32_t rc;
+  if ((rc = do_project_rows(c, L, n, x_dev, 0, n, 1))) return rc;  // message rows of every node
+  Ws w = carve(c, L, n);
+  {
+    LayerNormArgs ln;  // every row: LN(m); the active rows are overwritten below
+    ln.d = w.m; ln.ldd = w.ldm;
+    ln.m = w.m; ln.ldm = w.ldm;
+    ln.row_ptr = nullptr;
+    ln.gamma = L->gamma; ln.beta = L->beta; ln.eps = L->host.eps;
+    ln.out = out_dev;
+    ln.row_begin = 0; ln.row_end = n;
+    ln.H = H; ln.P = L->ord.P;
+    RUVGNN_CUDA_TRY(launch_layernorm(ln, c->stream, &c->launches));
+  }
+  if (timing) {
+    cudaEventRecord(c->ev[2], c->stream);
+    cudaEventRecord(c->ev[6], c->stream);
+    cudaEventRecord(c->ev[3], c->stream);
+  }
+  // compact buffers live in the (unused) per-node query region: Qc [B][hH] | Mc [B][H]; the
+  // per-block regions SA / T0..T3 are used as they are
+  const uint64_t B = na < upd_block() ? na : upd_block();
+  float *Qc = w.Qt, *Mc = w.Qt + (size_t)B * h * H;
+  const int64_t ldsa = (int64_t)(h + 1) * H;
+  for (uint64_t cb = 0; cb < na; cb += B) {
+    const uint64_t ce = cb + B < na ? cb + B : na;
+    RUVGNN_CUDA_TRY(launch_pack_rows(w.m, w.ldm, H, G->active_idx + cb, ce - cb, Mc, c->stream, &c->launches));
+    GemmArgs q;  // folded queries of the active rows
+    q.M = (int64_t)(ce - cb);
+    q.N = (int32_t)(h * H);
+    q.K1 = (int32_t)H;
+    q.A1 = Mc;
+    q.lda1 = H;
+    q.W = L->Wqk;
+    q.bias = L->bqk;
+    q.out = Qc;
+    q.ldo = (int64_t)h * H;
+    if ((rc = run_gemm(c, L, q, EPI_BIAS, TC_W_QKV))) return rc;
+    GatherR1Args ga;  // compact row i = node active_idx[i]; neighbours address the full message table
+    ga.M = w.m;
+    ga.ldm = w.ldm;
+    ga.halo = nullptr;
+    ga.n_local = n;
+    ga.Qt = Qc - (ptrdiff_t)(cb * (uint64_t)h * H);
+    ga.row_ptr = G->row_ptr_active;
+    ga.col_idx = G->col_idx;
+    ga.edge_w = G->edge_w;
+    ga.sa = w.SA - (ptrdiff_t)(cb * (uint64_t)ldsa);
+    ga.row_begin = cb;
+    ga.row_end = ce;
+    ga.heads = h;
+    ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
+    RUVGNN_CUDA_TRY(launch_gather_r1(ga, c->sm_count, c->stream, &c->launches));
+    UpdIO io;
+    io.oa = w.SA - (ptrdiff_t)(cb * (uint64_t)ldsa);
+    io.m = Mc - (ptrdiff_t)(cb * H);
+    io.ldm = H;
+    io.T0 = w.T0 - (ptrdiff_t)(cb * H);
+    io.T1 = w.T1 - (ptrdiff_t)(cb * H);
+    io.T2 = w.T2 - (ptrdiff_t)(cb * H);
+    io.T3 = w.T3 - (ptrdiff_t)(cb * H);
+    io.row_ptr = nullptr;  // every compact row has neighbours
+    io.scatter = G->active_idx;
+    io.out = out_dev;
+    if ((rc = update_rows_io(c, L, io, cb, ce))) return rc;
+  }
+  invalidate_projection(c);  // the workspace does not hold a full projection
+  return RUVGNN_OK;
+}
+
+int32_t forward_device(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G, const float *x_dev,
+                       float *out_dev, bool timing) {
+  const uint64_t n = G->n_nodes;
+  int32_t rc;
+  if (L->r1 && G->active_idx && L->heads <= 4) return forward_sparse_level(c, L, G, x_dev, out_dev, timing);
+  if ((rc = do_project(c, L, n, x_dev))) return rc;
+  if (timing) cudaEventRecord(c->ev[2], c->stream);
+  return do_aggregate_update(c, L, G, nullptr, 0, n, out_dev);
 }
 
 // Phase B over rows [rb, re): one K-agg -> K-upd pass per block of at most upd_block() rows.
@@ -880,6 +988,10 @@ int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
     if (g->row_ptr) cudaFree(g->row_ptr);
     if (g->col_idx) cudaFree(g->col_idx);
     if (g->edge_w) cudaFree(g->edge_w);
+    if (g->active_idx) cudaFree(g->active_idx);
+    if (g->row_ptr_active) cudaFree(g->row_ptr_active);
+    g->active_idx = nullptr;
+    g->row_ptr_active = nullptr;
     g->row_ptr = nullptr;
     g->col_idx = nullptr;
     g->edge_w = nullptr;
@@ -908,13 +1020,43 @@ int32_t ruvgnn_graph_create(ruvgnn_ctx *ctx, uint64_t n_nodes, uint64_t n_cols,
   int flag = 0;
   GTRY(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GTRY(cudaStreamSynchronize(ctx->stream));
-#undef GTRY
   if (flag) {
     cleanup();
     return fail(RUVGNN_ERR_INVALID_INPUT,
                 (flag & 1) ? "row_ptr is not monotone non-decreasing"
                            : "col_idx entry out of range (>= n_cols)");
   }
+  // sparse level: list the rows that have neighbours when they are fewer than half of all rows
+  if (n_nodes >= 1024 && n_cols == n_nodes && !(flags & RUVGNN_GRAPH_NO_ACTIVE_LIST)) {
+    std::vector<uint64_t> hrp;
+    const uint64_t *rp = row_ptr;
+    if (dev_ptrs) {
+      hrp.resize(n_nodes + 1);
+      GTRY(cudaMemcpy(hrp.data(), g->row_ptr, (n_nodes + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      rp = hrp.data();
+    }
+    uint64_t na = 0;
+    for (uint64_t i = 0; i < n_nodes; ++i) na += rp[i + 1] > rp[i];
+    if (na * 2 < n_nodes) {
+      std::vector<uint32_t> idx(na ? na : 1);
+      std::vector<uint64_t> rpa(na + 1);
+      uint64_t k = 0;
+      for (uint64_t i = 0; i < n_nodes; ++i)
+        if (rp[i + 1] > rp[i]) {
+          idx[k] = (uint32_t)i;
+          rpa[k] = rp[i];
+          ++k;
+        }
+      rpa[na] = n_edges;
+      // rows between two active rows are empty, so the CSR offsets of consecutive active rows abut
+      GTRY(cudaMalloc(&g->active_idx, (na + 4) * sizeof(uint32_t)));
+      GTRY(cudaMalloc(&g->row_ptr_active, (na + 1) * sizeof(uint64_t)));
+      GTRY(cudaMemcpy(g->active_idx, idx.data(), na * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      GTRY(cudaMemcpy(g->row_ptr_active, rpa.data(), (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+      g->n_active = na;
+    }
+  }
+#undef GTRY
   *out = g.release();
   return RUVGNN_OK;
   RUVGNN_ABI_CATCH
@@ -957,6 +1099,8 @@ void ruvgnn_graph_destroy(ruvgnn_graph *g) {
     if (g->col_idx) cudaFree(g->col_idx);
     if (g->edge_w) cudaFree(g->edge_w);
   }
+  if (g->active_idx) cudaFree(g->active_idx);
+  if (g->row_ptr_active) cudaFree(g->row_ptr_active);
   delete g;
 }
 
@@ -996,9 +1140,7 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   }
   if (dev_ptrs) {
     if (timing) cudaEventRecord(c->ev[1], c->stream);
-    if ((rc = do_project(c, L, n, x_dev))) return rc;
-    if (timing) cudaEventRecord(c->ev[2], c->stream);
-    if ((rc = do_aggregate_update(c, L, G, nullptr, 0, n, out_dev))) return rc;
+    if ((rc = forward_device(c, L, G, x_dev, out_dev, timing))) return rc;
     if (timing) {
       cudaEventRecord(c->ev[4], c->stream);
       cudaEventRecord(c->ev[5], c->stream);
@@ -1117,9 +1259,7 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
       cudaEventRecord(c->ev[0], c->stream);
       cudaEventRecord(c->ev[1], c->stream);
     }
-    if ((rc = do_project(c, layers[l], n, cur))) return rc;
-    if (timing) cudaEventRecord(c->ev[2], c->stream);
-    if ((rc = do_aggregate_update(c, layers[l], graphs[l], nullptr, 0, n, dst))) return rc;
+    if ((rc = forward_device(c, layers[l], graphs[l], cur, dst, timing))) return rc;
     if (timing) {
       cudaEventRecord(c->ev[4], c->stream);
       cudaEventRecord(c->ev[5], c->stream);

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LayerNormArgs a) {
     bool iso = false;
     if (a.row_ptr) iso = a.row_ptr[row] == a.row_ptr[row + 1];
     const float *src = iso ? a.m + row * (uint64_t)a.ldm : a.d + row * (uint64_t)a.ldd;
-    float *dst = a.out + row * (uint64_t)H;
+    float *dst = a.out + (a.scatter ? (uint64_t)a.scatter[row] : row) * (uint64_t)H;
     float s = 0.f;
     for (int t = lane; t < H; t += 32) s += src[t];
     const float mean = warp_sum(s) * invH;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) layernorm_fast_kernel(LayerNormArgs a) {
       v = fmaf(x[i].x, x[i].x, fmaf(x[i].y, x[i].y, fmaf(x[i].z, x[i].z, fmaf(x[i].w, x[i].w, v))));
     }
     const float denom = sqrtf(warp_sum(v) * invH + a.eps);
-    float4 *d4 = reinterpret_cast<float4 *>(a.out + row * (uint64_t)H);
+    float4 *d4 = reinterpret_cast<float4 *>(a.out + (a.scatter ? (uint64_t)a.scatter[row] : row) * (uint64_t)H);
 #pragma unroll
     for (int i = 0; i < P; ++i) {  // phys float4 index i*32+lane holds logical float4 lane*P+i
       float4 o;

@@ -191,3 +191,50 @@ def test_world_of_one_is_the_single_gpu_forward(built):
     assert np.array_equal(od.cpu().numpy(), want)
     assert d_.last_stats()["passes"] == 1
     torch.cuda.set_stream(torch.cuda.default_stream())
+
+
+@pytest.mark.parametrize("level,m", [(1, 8), (2, 8), (1, 32)])
+def test_sparse_level_equals_the_dense_path_bit_for_bit(built, oracle, level, m):
+    """Upper HNSW levels: only ~n / M^level rows have neighbours.  The active-row form (Q projection, gather
+    and update on those rows alone, LN(W_msg x + b) for the rest -- layer.rs:385-389) must return the bits of
+    the dense path, which is the oracle-checked one."""
+    import ruvector_b200 as rv
+    from ruvector_b200 import _lib, synth
+
+    ctx = rv.Context(0)
+    n, d, heads = 30000, 128, 4
+    g = synth.hnsw_like_graph(n, m, seed=level * 100 + m, level=level)
+    assert 0 < (g.degrees() > 0).sum() < n // 2
+    x = synth.make_features(n, d, seed=5)
+    layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=level), ctx=ctx)
+    dense = layer.forward_graph(x, g.to_device(ctx, flags=_lib.GRAPH_NO_ACTIVE_LIST))
+    # host buffers go through the row-block pipeline (dense); device buffers take the active-row form
+    import torch
+
+    with torch.cuda.stream(ctx.torch_stream()):
+        xd = torch.from_numpy(x).cuda()
+        od = torch.full((n, d), float("nan"), device="cuda")
+        dg = g.to_device(ctx)
+        layer.forward_graph_device(xd.data_ptr(), od.data_ptr(), dg, asynchronous=False)
+        sparse = od.cpu().numpy()
+    assert np.array_equal(sparse, dense)
+    assert row_rel(sparse, oracle.forward_graph(layer, x, g)) <= 1e-4
+
+
+def test_stack_over_levels_uses_sparse_levels_and_matches_the_oracle(built, oracle):
+    """Config-3 shape in small: three layers over levels 2, 1, 0 (search.rs:116-159 order); levels 2 and 1 run
+    the active-row form inside ruvgnn_stack_forward."""
+    import ruvector_b200 as rv
+    from ruvector_b200 import synth
+
+    ctx = rv.Context(0)
+    n, d, heads, m = 40000, 128, 4, 8
+    levels = [2, 1, 0]
+    gs = [synth.hnsw_like_graph(n, m, seed=77, level=lv) for lv in levels]
+    x = synth.make_features(n, d, seed=6)
+    layers = [rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=40 + l), ctx=ctx) for l in range(3)]
+    got = rv.forward_stack(layers, x, [g.to_device(ctx) for g in gs])
+    ref = x
+    for l, g in zip(layers, gs):
+        ref = oracle.forward_graph(l, ref, g)
+    assert row_rel(got, ref) <= 1e-4
