@@ -2,6 +2,10 @@
 //
 //   C[M x N] = [A1 | A2] * W^T + fused epilogue      (same contract as gemm_simt.cu)
 //
+// Two kernels share the warp roles below: this file's (A and B operands in shared memory) and
+// gemm_tc3.cu's (A operand in TMEM); launch_gemm_tc picks per weight matrix.  The cta_group::2
+// CTA-pair variants of round 1 never beat them (per-k-block cross-SM handshakes) and were removed.
+//
 // replaces the batched Linear::forward mat-vecs of crates/ruvector-gnn/src/layer.rs:37-41
 // (w_msg :392, q/k/v :135-137, out :159, w_agg :408, the six GRU linears :255-275).
 //
@@ -204,7 +208,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // row t of the k-block `dist` k-blocks ahead (one 128-byte line per producer thread), towards L2
+    auto prefetch_ahead = [&](int tile, int kb) {
+      int tt = tile, k = kb + p.pf_dist;
+      while (k >= num_kb) {
+        k -= num_kb;
+        tt += gridDim.x;
+      }
+      if (tt >= num_tiles) return;
+      const int64_t row = (int64_t)(tt / p.num_n_tiles) * BLOCK_M + t;
+      if (row >= g.M) return;
+      const int k0 = k * BLOCK_K;
+      prefetch_l2(k0 < g.K1 ? g.A1 + row * g.lda1 + k0 : g.A2 + row * g.lda2 + (k0 - g.K1));
+    };
     int tile = blockIdx.x, kb = 0;
+    if (p.pf_dist > 0 && tile < num_tiles && !(p.debug & 1))
+      for (int k = 1 - p.pf_dist; k < 0; ++k) prefetch_ahead(tile, k);
     if (tile < num_tiles && !(p.debug & 1)) issue(nxt, tile, 0);
     if (p.debug & 1)
       for (int i = 0; i < CH; ++i) nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -217,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         ntile = tile + gridDim.x;
       }
       if (ntile < num_tiles && !(p.debug & 1)) issue(nxt, ntile, nkb);
+      if (p.pf_dist > 0 && !(p.debug & 1)) prefetch_ahead(tile, kb);
       mbar_wait(&sm.empty[stage], phase ^ 1);
       uint8_t *hi = sm.a_hi[stage], *lo = sm.a_lo[stage];
 #pragma unroll
@@ -322,17 +342,6 @@ int pick_block_n(uint32_t n) {
 
 // k-block size of the 1-CTA kernel: 32 floats (128-byte rows) by default; RUVGNN_TC_BK=16
 // selects 64-byte rows (more, smaller stages) -- measured slower, kept for experiments.
-// CTA-pair (cta_group::2) kernel: correct (tests run it) but measured ~7% slower than the
-// 1-CTA kernel at config 2 (the per-k-block handshake crosses the cluster), so it is opt-in:
-// RUVGNN_TC_PAIR=1.
-bool tc_pair_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("RUVGNN_TC_PAIR");
-    on = (e && atoi(e) == 1) ? 1 : 0;
-  }
-  return on == 1;
-}
 int tc_block_k() {
   static int bk = 0;
   if (!bk) {
@@ -373,6 +382,15 @@ cudaError_t launch_epi(const CUtensorMap &hi, const CUtensorMap &lo, const TcPar
 }  // namespace
 
 namespace tc {
+int tc_pf_dist() {
+  static int d = -1;
+  if (d < 0) {
+    const char *e = getenv("RUVGNN_TC_PF");
+    d = e ? atoi(e) : 4;
+    if (d < 0 || d > 64) d = 4;
+  }
+  return d;
+}
 int tc_epi_mask() {
   static int mask = -1;
   if (mask < 0) {
@@ -444,20 +462,6 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
         return cudaErrorInvalidValue;
       }
     }
-    // CTA-pair kernel: each CTA streams half of the column tile (box {32, block_n/2})
-    maps->pair_ok[i] = false;
-    const cuuint32_t box2[2] = {32u, (cuuint32_t)(maps->block_n[i] / 2)};
-    if (maps->block_n[i] % 32 == 0) {
-      CUresult r1 = encode(&maps->hi2[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->hi[i], dims,
-                           strides, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      CUresult r2 = encode(&maps->lo2[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->lo[i], dims,
-                           strides, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      maps->pair_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
-    }
     // A-in-TMEM kernel: column tiles of at most 192 so two A stages fit beside the accumulators
     maps->ts_ok[i] = false;
     maps->block_n3[i] = pick_block_n_ts(rows[i]);
@@ -472,19 +476,6 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       maps->ts_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
-    }
-    maps->pair_ts_ok[i] = false;
-    if (maps->block_n3[i] > 0 && maps->block_n3[i] % 32 == 0) {
-      const cuuint32_t box4[2] = {32u, (cuuint32_t)(maps->block_n3[i] / 2)};
-      CUresult r1 = encode(&maps->hi4[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->hi[i], dims,
-                           strides, box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      CUresult r2 = encode(&maps->lo4[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out->lo[i], dims,
-                           strides, box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      maps->pair_ts_ok[i] = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
     }
   }
   out->tmaps = maps;
@@ -519,19 +510,11 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
       const char *e = getenv("RUVGNN_TC_TS");
       ts = e ? atoi(e) : -1;
     }
-    if (ts == 2 && maps->pair_ts_ok[which] && sm_count >= 2) {  // RUVGNN_TC_TS=2: pair + TMEM-A
-      if (launches) ++*launches;
-      return launch_gemm_tc_pair_ts(g, epi, *maps, which, single_pass, sm_count, s);
-    }
     const bool use_ts = ts == 1 || (ts == -1 && maps->block_n3[which] == maps->block_n[which]);
     if (use_ts && maps->ts_ok[which]) {
       if (launches) ++*launches;
       return launch_gemm_tc_ts(g, epi, *maps, which, single_pass, sm_count, s);
     }
-  }
-  if (tc_pair_enabled() && maps->pair_ok[which] && sm_count >= 2) {
-    if (launches) ++*launches;
-    return launch_gemm_tc_pair(g, epi, *maps, which, single_pass, sm_count, s);
   }
   const int BLOCK_K = maps->block_k;
   const int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;
@@ -547,6 +530,7 @@ cudaError_t launch_gemm_tc(const GemmArgs &g, EpiKind epi, const TcWeights &w, i
     }
     p.debug = dbg;
   }
+  p.pf_dist = tc_pf_dist();
   p.num_m_tiles = (int)((g.M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_tiles = g.N / p.block_n;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.block_n * BLOCK_K * 4;

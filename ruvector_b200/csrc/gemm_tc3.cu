@@ -208,8 +208,23 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap map_hi,
         for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // this thread's 128-byte slice of the k-block `dist` k-blocks ahead, pulled towards L2
+    auto prefetch_ahead = [&](int tile, int kb) {
+      int t = tile, k = kb + p.pf_dist;
+      while (k >= num_kb) {
+        k -= num_kb;
+        t += gridDim.x;
+      }
+      if (t >= num_tiles) return;
+      const int64_t row = (int64_t)(t / p.num_n_tiles) * BLOCK_M + row_in_tile;
+      if (row >= g.M) return;
+      const int k0 = k * BK;
+      prefetch_l2(k0 < g.K1 ? g.A1 + row * g.lda1 + k0 : g.A2 + row * g.lda2 + (k0 - g.K1));
+    };
     int tile = blockIdx.x, kb = 0;
     if (tile < num_tiles) issue(nxt, tile, 0);
+    if (p.pf_dist > 0 && tile < num_tiles)
+      for (int k = 1 - p.pf_dist; k < 0; ++k) prefetch_ahead(tile, k);  // k-blocks 1 .. dist-1 of the first tile
     while (tile < num_tiles) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
@@ -219,6 +234,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap map_hi,
         ntile = tile + gridDim.x;
       }
       if (ntile < num_tiles) issue(nxt, ntile, nkb);
+      if (p.pf_dist > 0) prefetch_ahead(tile, kb);
       mbar_wait(&empty_a[stage], phase ^ 1);
       tc_fence_after();
       const uint32_t ah = tmem_base + lane_base + a_col0 + (uint32_t)(stage * 64);
@@ -314,6 +330,7 @@ cudaError_t launch_gemm_tc_ts(const GemmArgs &g, EpiKind epi, const TcMaps &maps
   p.block_n = maps.block_n3[which];
   p.single_pass = single_pass ? 1 : 0;
   p.debug = 0;
+  p.pf_dist = tc_pf_dist();
   p.num_m_tiles = (int)((g.M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_tiles = g.N / p.block_n;
   p.stages = 0;

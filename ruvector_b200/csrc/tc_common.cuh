@@ -1,4 +1,4 @@
-// Shared device helpers of the tcgen05 GEMM kernels (1-CTA and CTA-pair variants).
+// Shared device helpers of the tcgen05 GEMM kernels (operands in shared memory / A operand in TMEM).
 #pragma once
 #include <cuda.h>
 
@@ -17,6 +17,10 @@ struct TcParams {
   int stages;
   int single_pass;
   int num_m_tiles, num_n_tiles;
+  int pf_dist;  // A-operand L2 prefetch distance in k-blocks (0: off).  Short-K GEMMs (H = 128) keep too few
+                // bytes in flight per SM with one k-block of register prefetch (16 KB against the ~43 KB that
+                // 6.4 TB/s x ~1 us needs): pulling the rows a few k-blocks ahead into L2 turns the HBM latency
+                // the producers see into L2 latency.
   int debug;  // timing experiments only (RUVGNN_TC_DEBUG): 1 = skip A loads/stores, 2 = skip weight TMA,
               // 4 = skip the MMAs, 8 = skip the epilogue's global traffic.  Results are garbage.
 };
@@ -331,18 +335,20 @@ __device__ __forceinline__ void epilogue_chunk_rowwise(const GemmArgs &g, int64_
   }
 
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// RUVGNN_TC_PF: prefetch distance in k-blocks (default 4, 0 = off)
+int tc_pf_dist();
+
 // Host: tensor maps of a layer's weight matrices.
 struct TcMaps {
   CUtensorMap hi[TC_W_COUNT], lo[TC_W_COUNT];    // box {block_k, block_n}
-  CUtensorMap hi2[TC_W_COUNT], lo2[TC_W_COUNT];  // box {32, block_n/2}: CTA-pair kernel
   CUtensorMap hi3[TC_W_COUNT], lo3[TC_W_COUNT];  // box {32, block_n3}: A-in-TMEM kernel
-  CUtensorMap hi4[TC_W_COUNT], lo4[TC_W_COUNT];  // box {32, block_n3/2}: pair + A-in-TMEM kernel
   int block_n[TC_W_COUNT];
   int block_n3[TC_W_COUNT];
   int block_k;
-  bool pair_ok[TC_W_COUNT];
   bool ts_ok[TC_W_COUNT];
-  bool pair_ts_ok[TC_W_COUNT];
 };
 
 // Which epilogue kinds use the coalesced (smem-transposed) form: bit e = EpiKind e.
@@ -353,14 +359,6 @@ int tc_epi_mask();
 int pick_block_n_ts(uint32_t n);
 cudaError_t launch_gemm_tc_ts(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
                               bool single_pass, int sm_count, cudaStream_t s);
-
-// CTA-pair + A-in-TMEM launcher, gemm_tc4.cu
-cudaError_t launch_gemm_tc_pair_ts(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
-                                   bool single_pass, int sm_count, cudaStream_t s);
-
-// CTA-pair (cta_group::2) launcher, gemm_tc2.cu
-cudaError_t launch_gemm_tc_pair(const GemmArgs &g, EpiKind epi, const TcMaps &maps, int which,
-                                bool single_pass, int sm_count, cudaStream_t s);
 
 }  // namespace tc
 }  // namespace ruvgnn
