@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--locality", type=float, default=0.0)
     ap.add_argument("--window", type=int, default=4096, help="id window of the local neighbours (with --locality)")
     ap.add_argument("--exact", action="store_true", help="N>1: single-pass gather after the halo landed (bit-identical to 1 GPU)")
-    ap.add_argument("--chunks", type=int, default=0, help="N>1: row chunks of the dense plane (0: 4 for K|V|M halos, 2 for message rows)")
+    ap.add_argument("--chunks", type=int, default=0, help="N>1: row chunks of the dense plane (0: the library's choice from the world size)")
     ap.add_argument("--mode", type=int, default=-1, help="-1: the library default (tcgen05 3xTF32 where the shape allows)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -418,7 +418,7 @@ def secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
     world, rank = h.world, h.rank
     ctx = rv.Context(h.local, h.stream.cuda_stream)
     dist_ = rvdist.Dist.from_env(ctx)
-    dist_.set_chunks(a.chunks or 2)
+    dist_.set_chunks(a.chunks)
     layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d), ctx=ctx)
     slab = 1 << 21
     n_pad = (n + slab - 1) // slab * slab  # feature slabs are addressed by global slab id
@@ -449,6 +449,11 @@ def secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
         t = ctx.last_timing()
         ctx.set_timing(False)
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
+        # the same partition in exact mode (single-pass gather after the halo landed; bit-identical to 1 GPU)
+        ms_exact = None
+        if not a.exact:
+            ms_exact = h.timed(lambda: part.forward(layer, x, out, exact=True), 3, 1)
+            stats_exact = dist_.last_stats()
         # self-check without the oracle: the overlapped multi-pass result against the exact single-pass one
         check = None
         if not a.exact:
@@ -469,6 +474,10 @@ def secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
                "roofline_projections": gemm_roofline(d, d, heads, R, float(n), float(stage[0] + stage[2]), passes,
                                                      hbm_peak, tf32_peak, tf32_src),
                "halo": halo_block(part, dist_, stats, "overlapped multi-pass"), "check": check,
+               "exact_mode": None if ms_exact is None else {
+                   "ms_per_step": ms_exact, "value": n * world / (ms_exact * 1e-3),
+                   "exposed_wait_ms_rank0": round(stats_exact["exposed_wait_ms"], 3),
+                   "exchange_ms_rank0": round(stats_exact["exchange_ms"], 3)},
                "hbm_used_gb_rank0": h.mem_used_gb()}
         blk["roofline"]["note"] = "K-agg time summed over the gather passes; bytes = the single-pass algorithmic bytes"
         blocks[f"locality_{lam}"] = blk
@@ -510,7 +519,7 @@ def main():
             from ruvector_b200 import dist as rvdist
 
             dist_ = rvdist.Dist.from_env(ctx)
-            dist_.set_chunks(a.chunks or (2 if R == 1 else 4))
+            dist_.set_chunks(a.chunks)
             part = rvdist.Partition.from_graph(dist_, g, a.nodes)
             step_fn = lambda xd, od: part.forward(layer, xd, od, exact=a.exact)
             dg = None

@@ -121,7 +121,7 @@ struct ruvgnn_dist {
   uint32_t waits_used = 0;
   float *send = nullptr, *halo = nullptr;
   size_t send_floats = 0, halo_floats = 0;
-  uint32_t chunks = 4;
+  uint32_t chunks = 0;  // 0: chosen from the world size when a partition is created
   bool offline = false;  // world > 1 without a communicator: plans can be built, nothing exchanged
   ruvgnn_dist_stats stats = {};
   bool stats_valid = false;
@@ -500,8 +500,8 @@ int32_t ruvgnn_dist_info(const ruvgnn_dist *d, int32_t *rank, int32_t *world) {
 int32_t ruvgnn_dist_set_chunks(ruvgnn_dist *d, uint32_t chunks) {
   RUVGNN_ABI_TRY
   if (!d) return fail(RUVGNN_ERR_INVALID_INPUT, "dist is null");
-  if (chunks < 1 || chunks > (uint32_t)kMaxChunks)
-    return fail(RUVGNN_ERR_INVALID_INPUT, "chunks must be in [1, 16]");
+  if (chunks > (uint32_t)kMaxChunks)
+    return fail(RUVGNN_ERR_INVALID_INPUT, "chunks must be in [0, 16] (0: chosen from the world size)");
   d->chunks = chunks;
   return RUVGNN_OK;
   RUVGNN_ABI_CATCH
@@ -662,7 +662,10 @@ int32_t ruvgnn_partition_create(ruvgnn_dist *d, const uint64_t *bounds, const ui
   P->dense = dense;
 
   if (dense) {
-    uint32_t chunks = d->chunks;
+    // Each chunk costs one more gather pass (state re-read, ragged edge groups), so chunks pay off
+    // only while the wire time they hide exceeds that: with 2 ranks the pass over the own-row
+    // edges alone outlasts the exchange (1 chunk); with 8 the exchange dominates (4 chunks).
+    uint32_t chunks = d->chunks ? d->chunks : (world <= 2 ? 1u : world <= 4 ? 2u : 4u);
     if ((uint64_t)chunks > n) chunks = (uint32_t)(n ? n : 1);
     P->starts.resize(chunks + 1);
     for (uint32_t k = 0; k <= chunks; ++k) P->starts[k] = (n * k) / chunks;
