@@ -96,12 +96,15 @@ struct GatherArgs {
   uint64_t row_begin = 0, row_end = 0;
   uint32_t H = 0, heads = 0;
   int prenormalized = 0;
-  // Multi-pass gather (partitioned forward, dist.cu): this launch handles only the edges whose
-  // column lies in [col_lo, col_hi).  first: the state starts from zero; otherwise it is read
-  // back from oa (raw accumulators o | agg) and ml ([row][2*heads]: running max, running sum per
-  // head).  last: oa receives the normalised o | agg that K-upd reads; otherwise the raw state.
+  // Multi-pass gather (partitioned forward, dist.cu): col_idx / edge_w are the pass-ordered copy of
+  // the edge arrays (launch_build_pass_csr; weights already normalised) and this launch handles
+  // group `pass` of every row, edges row_ptr[row] + [seg[row][pass], seg[row][pass+1]).  first: the
+  // state starts from zero; otherwise it is read back from oa (raw accumulators o | agg) and ml
+  // ([row][2*heads]: running max, running sum per head).  last: oa receives the normalised o | agg
+  // that K-upd reads; otherwise the raw state.
   int multipass = 0, first = 1, last = 1;
-  uint64_t col_lo = 0, col_hi = ~0ull;
+  const uint32_t *seg = nullptr;  // [rows][npass1]
+  int npass1 = 0, pass = 0;
   float *ml = nullptr;
 };
 cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
@@ -128,10 +131,18 @@ struct GatherR1Args {
   int prenormalized = 0;
   // multi-pass gather, as in GatherArgs (state: sa raw S_g | agg, ml [row][2*heads])
   int multipass = 0, first = 1, last = 1;
-  uint64_t col_lo = 0, col_hi = ~0ull;
+  const uint32_t *seg = nullptr;
+  int npass1 = 0, pass = 0;
   float *ml = nullptr;
 };
 cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s, uint64_t *launches);
+// Pass-ordered copy of a CSR's edge arrays for the multi-pass gather: pass p = the columns in
+// [bounds[p], bounds[p+1]) (bounds_dev: npass + 1 ascending device values covering every column);
+// col_p / w_p: [n_edges] (w_p normalised by the aggregate_messages rule); seg: [n_rows][npass + 1].
+cudaError_t launch_build_pass_csr(const uint64_t *row_ptr, const uint32_t *col, const float *w,
+                                  uint64_t n_rows, const uint64_t *bounds_dev, int npass,
+                                  int prenormalized, uint32_t *col_p, float *w_p, uint32_t *seg,
+                                  cudaStream_t s, uint64_t *launches);
 
 // ---- row ops ----------------------------------------------------------------
 // out[row] = LayerNorm(deg(row) > 0 ? d[row] : m[row]), written in logical order.

@@ -139,6 +139,7 @@ struct ruvgnn_partition {
   std::vector<uint64_t> starts;  // dense plane: row chunk boundaries
   std::vector<std::pair<uint64_t, uint64_t>> interior, boundary;
   uint64_t interior_rows = 0;
+  PassCsr pass;  // pass-ordered edge arrays of the overlapped forward: own rows, then one group per chunk
 };
 
 namespace {
@@ -372,6 +373,23 @@ int32_t ensure_buf(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
   return RUVGNN_OK;
 }
 
+// Pass-ordered copy of G's edge arrays for the column bounds given (host, npass + 1 ascending values).
+int32_t build_pass_csr(ruvgnn_ctx *c, const ruvgnn_graph *G, const std::vector<uint64_t> &bounds, PassCsr *out) {
+  const int npass = (int)bounds.size() - 1;
+  DevMem d_bounds;
+  RUVGNN_CUDA_TRY(d_bounds.alloc(bounds.size() * 8));
+  RUVGNN_CUDA_TRY(cudaMemcpyAsync(d_bounds.p, bounds.data(), bounds.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  RUVGNN_CUDA_TRY(cudaMalloc(&out->col, (G->n_edges + 4) * sizeof(uint32_t)));
+  RUVGNN_CUDA_TRY(cudaMalloc(&out->w, (G->n_edges + 4) * sizeof(float)));
+  RUVGNN_CUDA_TRY(cudaMalloc(&out->seg, (G->n_nodes * (uint64_t)(npass + 1) + 4) * sizeof(uint32_t)));
+  out->npass = npass;
+  RUVGNN_CUDA_TRY(launch_build_pass_csr(G->row_ptr, G->col_idx, G->edge_w, G->n_nodes, d_bounds.as<uint64_t>(),
+                                        npass, (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0, out->col, out->w,
+                                        out->seg, c->stream, &c->launches));
+  RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RUVGNN_OK;
+}
+
 int32_t make_dist(ruvgnn_ctx *ctx, ncclComm_t comm, int rank, int world, ruvgnn_dist **out) {
   std::unique_ptr<ruvgnn_dist> d(new ruvgnn_dist());
   d->ctx = ctx;
@@ -515,6 +533,9 @@ void ruvgnn_partition_destroy(ruvgnn_partition *p) {
   if (p->graph.edge_w) cudaFree(p->graph.edge_w);
   if (p->need_ids) cudaFree(p->need_ids);
   if (p->send_idx) cudaFree(p->send_idx);
+  if (p->pass.col) cudaFree(p->pass.col);
+  if (p->pass.w) cudaFree(p->pass.w);
+  if (p->pass.seg) cudaFree(p->pass.seg);
   delete p;
 }
 
@@ -735,6 +756,18 @@ int32_t ruvgnn_partition_create(ruvgnn_dist *d, const uint64_t *bounds, const ui
     interior_runs(is_int, 1024, 4, P->interior, P->boundary);
     for (const auto &r : P->interior) P->interior_rows += r.second - r.first;
   }
+  // ---- pass-ordered edge arrays for the overlapped forward ---------------------------------------
+  if (world > 1 && n && !d->offline) {
+    std::vector<uint64_t> pb;  // column bounds of the passes: own rows, then one range per chunk
+    pb.push_back(0);
+    pb.push_back(n);
+    if (dense)
+      for (size_t k = 1; k < P->starts.size(); ++k) pb.push_back(n + (uint64_t)world * P->starts[k]);
+    else
+      pb.push_back(n + n_halo);
+    int32_t rc = build_pass_csr(c, &G, pb, &P->pass);
+    if (rc) return rc;
+  }
   RUVGNN_CUDA_TRY(cudaGetLastError());
   *out = P.release();
   return RUVGNN_OK;
@@ -794,7 +827,7 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   const uint32_t H = L->H, D = L->D, W = L->r1 ? H : 3 * H;
   const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
   const bool mp_ok = L->fast && (!L->r1 || L->heads <= 4);
-  const bool exact = (flags & RUVGNN_DIST_EXACT) || !mp_ok || world == 1;
+  const bool exact = (flags & RUVGNN_DIST_EXACT) || !mp_ok || world == 1 || !P->pass.col;
   const ruvgnn_graph *G = &P->graph;
   cudaStream_t s = c->stream, cs = d->comm_stream;
   int32_t rc;
@@ -957,8 +990,8 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   } else {
     // pass 0: the edges to own rows, for all rows, while the halo is on the wire
     GatherPass p0;
-    p0.col_lo = 0;
-    p0.col_hi = n;
+    p0.csr = &P->pass;
+    p0.index = 0;
     p0.first = true;
     p0.last = false;
     if (n && (rc = gather_rows(c, L, G, d->halo, 0, n, p0, true))) return rc;
@@ -966,15 +999,10 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
     for (uint32_t k = 0; k < n_chunks; ++k) {
       if ((rc = wait_chunk(k))) return rc;
       GatherPass pk;
+      pk.csr = &P->pass;
+      pk.index = (int)k + 1;
       pk.first = false;
       pk.last = k + 1 == n_chunks;
-      if (P->dense) {
-        pk.col_lo = n + (uint64_t)world * P->starts[k];
-        pk.col_hi = n + (uint64_t)world * P->starts[k + 1];
-      } else {
-        pk.col_lo = n;
-        pk.col_hi = n + P->n_halo;
-      }
       if (!pk.last) {
         if (n && (rc = gather_rows(c, L, G, d->halo, 0, n, pk, true))) return rc;
       } else if ((rc = finish_range(0, n, pk))) {
@@ -1046,20 +1074,29 @@ int32_t ruvgnn_layer_forward_split(ruvgnn_ctx *c, const ruvgnn_layer *L, const r
   DeviceGuard dg(c->device);
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = false;
+  std::vector<uint64_t> pb;
+  pb.push_back(0);
+  for (uint32_t i = 0; i < n_splits; ++i) pb.push_back(splits[i]);
+  pb.push_back(G->n_cols);
+  PassCsr pc;
+  int32_t rc = n_splits ? build_pass_csr(c, G, pb, &pc) : RUVGNN_OK;
   c->state_per_node = true;
-  int32_t rc = do_project(c, L, n, x_dev);
+  if (!rc) rc = do_project(c, L, n, x_dev);
   for (uint32_t i = 0; i <= n_splits && !rc; ++i) {
     GatherPass p;
-    p.col_lo = i ? splits[i - 1] : 0;
-    p.col_hi = i < n_splits ? splits[i] : G->n_cols;
+    p.csr = n_splits ? &pc : nullptr;
+    p.index = (int)i;
     p.first = i == 0;
     p.last = i == n_splits;
-    if (n_splits == 0) p.col_hi = ~0ull;
     if (!p.last)
       rc = gather_rows(c, L, G, nullptr, 0, n, p, false);
     else
       rc = do_aggregate_update(c, L, G, nullptr, 0, n, out_dev, false, p);
   }
+  cudaStreamSynchronize(c->stream);
+  if (pc.col) cudaFree(pc.col);
+  if (pc.w) cudaFree(pc.w);
+  if (pc.seg) cudaFree(pc.seg);
   c->state_per_node = false;
   if (!rc) RUVGNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   invalidate_projection(c);

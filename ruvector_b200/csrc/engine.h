@@ -127,13 +127,22 @@ struct Ws {
   float *ML;  // [n][2*heads] running softmax (max, sum) per head; state_per_node only
 };
 
-// One pass of the gather over the edges whose column lies in [col_lo, col_hi).  first: the
-// gather state starts from zero; last: the state is normalised and written in the form K-upd
-// reads.  first && last over the full column range is the ordinary single-pass gather.
+// Pass-ordered copy of a graph's edge arrays (launch_build_pass_csr): every row's edges grouped by
+// gather pass, weights normalised, seg[row][0..npass] = the group offsets inside the row.
+struct PassCsr {
+  uint32_t *col = nullptr;
+  float *w = nullptr;
+  uint32_t *seg = nullptr;
+  int npass = 0;
+};
+// One pass of the gather.  csr == nullptr: the ordinary single-pass gather over the graph's own
+// edge arrays.  Otherwise group `index` of every row of the pass-ordered copy; first: the gather
+// state starts from zero; last: the state is normalised and written in the form K-upd reads.
 struct GatherPass {
-  uint64_t col_lo = 0, col_hi = ~0ull;
+  const PassCsr *csr = nullptr;
+  int index = 0;
   bool first = true, last = true;
-  bool whole() const { return first && last && col_lo == 0 && col_hi == ~0ull; }
+  bool whole() const { return csr == nullptr; }
 };
 
 uint64_t upd_block();

@@ -271,9 +271,15 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
     ga.H = H;
     ga.heads = L->heads;
     ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
-    ga.multipass = pass.whole() ? 0 : 1;
-    ga.col_lo = pass.col_lo;
-    ga.col_hi = pass.col_hi;
+    if (pass.csr) {
+      ga.multipass = 1;
+      ga.col_idx = pass.csr->col;
+      ga.edge_w = pass.csr->w;
+      ga.prenormalized = 1;
+      ga.seg = pass.csr->seg;
+      ga.npass1 = pass.csr->npass + 1;
+      ga.pass = pass.index;
+    }
     ga.first = pass.first ? 1 : 0;
     ga.last = pass.last ? 1 : 0;
     ga.ml = w.ML;
@@ -293,9 +299,15 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
     ga.row_end = re;
     ga.heads = L->heads;
     ga.prenormalized = (G->flags & RUVGNN_GRAPH_PRENORMALIZED) ? 1 : 0;
-    ga.multipass = pass.whole() ? 0 : 1;
-    ga.col_lo = pass.col_lo;
-    ga.col_hi = pass.col_hi;
+    if (pass.csr) {
+      ga.multipass = 1;
+      ga.col_idx = pass.csr->col;
+      ga.edge_w = pass.csr->w;
+      ga.prenormalized = 1;
+      ga.seg = pass.csr->seg;
+      ga.npass1 = pass.csr->npass + 1;
+      ga.pass = pass.index;
+    }
     ga.first = pass.first ? 1 : 0;
     ga.last = pass.last ? 1 : 0;
     ga.ml = w.ML;

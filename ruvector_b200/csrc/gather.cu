@@ -169,24 +169,51 @@ __global__ void __launch_bounds__(128) gather_fast_kernel(GatherArgs a, float in
 // ---- multi-pass variants (partitioned forward) --------------------------------------------
 // The partitioned forward splits a node's neighbour list by where the rows live (own rows,
 // then one column range per halo chunk as it arrives) and runs one gather pass per range while
-// the next chunk is still on the wire.  A pass handles the edges whose column lies in
-// [col_lo, col_hi), in stored order, and carries the online-softmax state (raw accumulators,
-// running max and running sum per head) to the next pass through oa / ml.  The merge is the same
-// rescaling the single-pass kernels apply edge by edge, so the result equals the single pass up
-// to f32 summation order (own tolerance, tests/test_gpu_multipass.py).
-//
-// Compaction: per 32-edge chunk the in-range lanes are counted with a ballot and the t-th
-// in-range edge is handed to slot t by shuffle (__fns), after which the unfiltered inner loops run
-// unchanged on the compacted (col, weight) list.
-__device__ __forceinline__ int compact32(bool in_range, uint32_t &col, float &w, int lane) {
-  const uint32_t mask = __ballot_sync(0xffffffffu, in_range);
-  const int cnt = __popc(mask);
-  const uint32_t src = __fns(mask, 0, lane + 1);  // lane of the (lane+1)-th in-range edge
-  const uint32_t from = src < 32u ? src : 0u;
-  col = __shfl_sync(0xffffffffu, col, from);
-  w = __shfl_sync(0xffffffffu, w, from);
-  if (lane >= cnt) w = 0.f;
-  return cnt;
+// the next chunk is still on the wire.  The split is made ONCE per graph: build_pass_csr_kernel
+// writes a second copy of the edge arrays in which every row's edges are stably grouped by pass
+// (stored order kept inside a group), with the edge weights already normalised by the rule of
+// aggregate_messages (layer.rs:426-432, the sum runs over ALL of the row's edges), and per row the
+// group offsets seg[row][0..npass].  A pass then walks one contiguous group per row with the inner
+// loops of the single-pass kernels -- no filtering, no compaction -- and carries the online-softmax
+// state (raw accumulators, running max and running sum per head) to the next pass through oa / ml.
+// Rows without edges in a middle pass are skipped outright.  The merge is the rescaling the
+// single-pass kernels apply edge by edge, so the result equals the single pass up to f32 summation
+// order (own tolerance, tests/test_gpu_multipass.py).
+__global__ void __launch_bounds__(256) build_pass_csr_kernel(const uint64_t *row_ptr, const uint32_t *col,
+                                                             const float *w, uint64_t n_rows,
+                                                             const uint64_t *bounds, int npass,
+                                                             int prenormalized, uint32_t *col_p,
+                                                             float *w_p, uint32_t *seg) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t row = warp; row < n_rows; row += nwarps) {
+    const uint64_t beg = row_ptr[row], end = row_ptr[row + 1];
+    uint32_t *sg = seg + row * (uint64_t)(npass + 1);
+    if (beg == end) {
+      for (int p = lane; p <= npass; p += 32) sg[p] = 0;
+      continue;
+    }
+    const WeightRule rule = make_rule(w, beg, end, lane, prenormalized);
+    uint32_t base = 0;
+    for (int p = 0; p < npass; ++p) {
+      if (lane == 0) sg[p] = base;
+      const uint64_t lo = bounds[p], hi = bounds[p + 1];
+      for (uint64_t c = beg; c < end; c += 32) {
+        const uint64_t e = c + lane;
+        const uint32_t cc = e < end ? col[e] : 0u;
+        const bool in = e < end && (uint64_t)cc >= lo && (uint64_t)cc < hi;
+        const uint32_t mask = __ballot_sync(0xffffffffu, in);
+        if (in) {
+          const uint64_t pos = beg + base + __popc(mask & ((1u << lane) - 1u));
+          col_p[pos] = cc;
+          w_p[pos] = rule.apply(w[e]);
+        }
+        base += __popc(mask);
+      }
+    }
+    if (lane == 0) sg[npass] = base;  // == degree when the bounds cover every column
+  }
 }
 
 template <int P, int LH, int U>
@@ -199,15 +226,20 @@ __global__ void __launch_bounds__(128) gather_fast_mp_kernel(GatherArgs a, float
   const int heads = 32 / LH, head = lane / LH;
 
   for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
-    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    const uint64_t beg0 = __ldg(a.row_ptr + node), end0 = __ldg(a.row_ptr + node + 1);
     float4 *orow = reinterpret_cast<float4 *>(a.oa + node * (uint64_t)(2 * H));
     float *ml = a.ml + node * (uint64_t)(2 * heads);
-    if (beg == end) {  // no neighbours: zeros in every pass (the update takes the LN(m) path)
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg0 == end0) {  // no neighbours: zeros (the update takes the LN(m) path)
+      if (a.first || a.last) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 2 * P; ++i) orow[i * 32 + lane] = zero;
+        for (int i = 0; i < 2 * P; ++i) orow[i * 32 + lane] = zero;
+      }
       continue;
     }
+    const uint32_t *sg = a.seg + node * (uint64_t)a.npass1;
+    const uint64_t beg = beg0 + __ldg(sg + a.pass), end = beg0 + __ldg(sg + a.pass + 1);
+    if (beg == end && !a.first && !a.last) continue;  // nothing to merge for this row in this pass
     const float4 *qrow = reinterpret_cast<const float4 *>(a.P + node * (uint64_t)a.ldp);
     float4 q[P], acc[P], ag[P];
     float mx = -INFINITY, l = 0.f;
@@ -228,7 +260,6 @@ __global__ void __launch_bounds__(128) gather_fast_mp_kernel(GatherArgs a, float
       mx = ml[head];
       l = ml[heads + head];
     }
-    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
 
     auto row_of = [&](uint32_t col) -> const float4 * {
       return (uint64_t)col < a.n_local
@@ -275,10 +306,9 @@ __global__ void __launch_bounds__(128) gather_fast_mp_kernel(GatherArgs a, float
 
     for (uint64_t c = beg; c < end; c += 32) {
       const uint64_t e = c + lane;
-      uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
-      float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
-      const bool inr = e < end && (uint64_t)my_col >= a.col_lo && (uint64_t)my_col < a.col_hi;
-      const int cnt = compact32(inr, my_col, my_w, lane);
+      const uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      const float my_w = e < end ? __ldg(a.edge_w + e) : 0.f;  // normalised when the pass CSR was built
+      const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
       int jj = 0;
       for (; jj + U <= cnt; jj += U) {
         RowRegs<P> r[U];
@@ -697,15 +727,20 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_mp_kernel(GatherR1Ar
   const int my_slot = lane >> 2;
   const int my_head = (lane / REP) % HEADS;
   for (uint64_t node = a.row_begin + warp; node < a.row_end; node += nwarps) {
-    const uint64_t beg = __ldg(a.row_ptr + node), end = __ldg(a.row_ptr + node + 1);
+    const uint64_t beg0 = __ldg(a.row_ptr + node), end0 = __ldg(a.row_ptr + node + 1);
     float4 *srow = reinterpret_cast<float4 *>(a.sa + node * (uint64_t)((HEADS + 1) * H));
     float *ml = a.ml + node * (uint64_t)(2 * HEADS);
-    if (beg == end) {
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg0 == end0) {
+      if (a.first || a.last) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int g = 0; g <= HEADS; ++g) srow[g * 32 + lane] = zero;
+        for (int g = 0; g <= HEADS; ++g) srow[g * 32 + lane] = zero;
+      }
       continue;
     }
+    const uint32_t *sg = a.seg + node * (uint64_t)a.npass1;
+    const uint64_t beg = beg0 + __ldg(sg + a.pass), end = beg0 + __ldg(sg + a.pass + 1);
+    if (beg == end && !a.first && !a.last) continue;  // nothing to merge for this row in this pass
     const float4 *qrow = reinterpret_cast<const float4 *>(a.Qt + node * (uint64_t)(HEADS * H));
     float4 qt[HEADS], S[HEADS];  // slot g: head g ^ my_head
     float4 ag = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -721,13 +756,11 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_mp_kernel(GatherR1Ar
       mx = ml[my_head];
       lsum = (my_slot == 0) ? ml[HEADS + my_head] : 0.f;  // the sum is re-split over the edge slots
     }
-    const WeightRule rule = make_rule(a.edge_w, beg, end, lane, a.prenormalized);
     for (uint64_t c = beg; c < end; c += 32) {
       const uint64_t e = c + lane;
-      uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
-      float my_w = e < end ? rule.apply(__ldg(a.edge_w + e)) : 0.f;
-      const bool inr = e < end && (uint64_t)my_col >= a.col_lo && (uint64_t)my_col < a.col_hi;
-      const int cnt = compact32(inr, my_col, my_w, lane);
+      const uint32_t my_col = e < end ? __ldg(a.col_idx + e) : 0u;
+      const float my_w = e < end ? __ldg(a.edge_w + e) : 0.f;  // normalised when the pass CSR was built
+      const int cnt = (end - c) < 32 ? (int)(end - c) : 32;
       for (int jj = 0; jj < cnt; jj += EB) {
         float4 r[EB];  // slot u: edge jj + (u ^ my_slot)
         if (jj + EB < cnt) {
@@ -889,6 +922,19 @@ cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cu
 }
 
 }  // namespace
+
+cudaError_t launch_build_pass_csr(const uint64_t *row_ptr, const uint32_t *col, const float *w,
+                                  uint64_t n_rows, const uint64_t *bounds_dev, int npass,
+                                  int prenormalized, uint32_t *col_p, float *w_p, uint32_t *seg,
+                                  cudaStream_t s, uint64_t *launches) {
+  if (n_rows == 0) return cudaSuccess;
+  if (launches) ++*launches;
+  uint64_t blocks = (n_rows + 7) / 8;
+  if (blocks > 148ull * 32) blocks = 148ull * 32;
+  build_pass_csr_kernel<<<(unsigned)blocks, 256, 0, s>>>(row_ptr, col, w, n_rows, bounds_dev, npass,
+                                                        prenormalized, col_p, w_p, seg);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s,
                              uint64_t *launches) {
