@@ -35,7 +35,7 @@ def make_features(n: int, d: int, seed: int = 0x5EED, device="cuda", row_offset:
     for a in range(0, n, slab):
         b = min(a + slab, n)
         g = _gen(seed * 1000003 + (row_offset + a) // slab, device)
-        x = torch.randn((min(slab, b - a), d), generator=g, dtype=torch.float32, device=device)
+        x = torch.randn((slab, d), generator=g, dtype=torch.float32, device=device)  # whole slabs: see feature_rows
         x /= x.norm(dim=1, keepdim=True).clamp_min(1e-12)
         out[a:b] = x[: b - a]
     return out
@@ -112,3 +112,21 @@ def hnsw_like_graph(n: int, m: int, seed: int = 0xBEEF, locality: float = 0.0, w
     col = torch.cat(cols_out) if cols_out else torch.zeros(0, dtype=torch.int32, device=device)
     w = torch.cat(w_out) if w_out else torch.zeros(0, dtype=torch.float32, device=device)
     return row_ptr, col.contiguous(), w.contiguous()
+
+
+def feature_rows(rows, d: int, seed: int = 0x5EED, device="cuda", slab: int = 1 << 21):
+    """The rows ``rows`` (indices in the slab-addressed row space of :func:`make_features`, i.e.
+    ``row_offset + r``) regenerated on their own: only the slabs that hold them are drawn."""
+    import numpy as np
+    import torch
+
+    rows = np.asarray(rows, dtype=np.int64)
+    out = torch.empty((rows.size, d), dtype=torch.float32, device=device)
+    for sid in np.unique(rows // slab):
+        sel = np.nonzero(rows // slab == sid)[0]
+        g = _gen(seed * 1000003 + int(sid), device)
+        x = torch.randn((slab, d), generator=g, dtype=torch.float32, device=device)
+        x /= x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        out[torch.as_tensor(sel, device=device)] = x[torch.as_tensor(rows[sel] - sid * slab, device=device)]
+        del x
+    return out
