@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--window", type=int, default=4096, help="id window of the local neighbours (with --locality)")
     ap.add_argument("--exact", action="store_true", help="N>1: single-pass gather after the halo landed (bit-identical to 1 GPU)")
     ap.add_argument("--chunks", type=int, default=0, help="N>1: row chunks of the dense plane (0: the library's choice from the world size)")
+    ap.add_argument("--msg-halo", action="store_true", help="N>1, K|V|M layers: ship message rows and rebuild K, V on arrival")
     ap.add_argument("--mode", type=int, default=-1, help="-1: the library default (tcgen05 3xTF32 where the shape allows)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -521,7 +522,7 @@ def main():
             dist_ = rvdist.Dist.from_env(ctx)
             dist_.set_chunks(a.chunks)
             part = rvdist.Partition.from_graph(dist_, g, a.nodes)
-            step_fn = lambda xd, od: part.forward(layer, xd, od, exact=a.exact)
+            step_fn = lambda xd, od: part.forward(layer, xd, od, exact=a.exact, msg_halo=a.msg_halo)
             dg = None
         else:
             dg = g.to_device(ctx)
@@ -565,7 +566,7 @@ def main():
             out_pin = torch.empty(n, H, dtype=torch.float32).pin_memory()
             x_np, out_np = x_pin.numpy(), out_pin.numpy()
             if world > 1:
-                e2e_fn = lambda: part.forward_host(layer, x_np, out_np, exact=a.exact)
+                e2e_fn = lambda: part.forward_host(layer, x_np, out_np, exact=a.exact, msg_halo=a.msg_halo)
             else:
                 e2e_fn = lambda: layer.forward_graph(x_np, dg, out=out_np)
             k2 = max(2, min(a.steps, 5))

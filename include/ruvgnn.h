@@ -389,8 +389,12 @@ int32_t ruvgnn_partition_download(const ruvgnn_partition *p, uint32_t *col_idx_l
  *               in HBM) -> update.  Equals the single-GPU result up to f32 summation order.
  *   RUVGNN_DIST_EXACT   single-pass gather after the whole halo has arrived, all-local row runs
  *               first: every row goes through exactly the arithmetic of the single-GPU run
- *               (bit-identical outputs). */
+ *               (bit-identical outputs).
+ *   RUVGNN_DIST_MSG_HALO   dense plane, K|V|M layers: peers ship the message rows only (a third of
+ *               the bytes) and K, V are rebuilt on arrival with the projection's own GEMM
+ *               (layer.rs:136-137), so a rebuilt row carries the owner's bits; ignored elsewhere. */
 #define RUVGNN_DIST_EXACT 16u
+#define RUVGNN_DIST_MSG_HALO 32u
 int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *p, const ruvgnn_layer *layer,
                             const float *x, float *out, uint32_t flags);
 typedef struct {

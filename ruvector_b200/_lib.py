@@ -115,7 +115,7 @@ class DistStats(C.Structure):
                 ("exchange_ms", C.c_float), ("passes", C.c_uint32), ("exact", C.c_uint32)]
 
 FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
-DIST_EXACT = 16
+DIST_EXACT, DIST_MSG_HALO = 16, 32
 PART_DEVICE_PTRS, PART_FORCE_SPARSE, PART_FORCE_DENSE = 1, 2, 4
 NCCL_ID_BYTES = 128
 GRAPH_PRENORMALIZED, GRAPH_DEVICE_PTRS, GRAPH_NO_ACTIVE_LIST = 1, 2, 4

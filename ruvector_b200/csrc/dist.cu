@@ -119,8 +119,8 @@ struct ruvgnn_dist {
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;  // comm stream: exchange start / end (timed)
   cudaEvent_t ev_w0[kMaxChunks] = {}, ev_w1[kMaxChunks] = {};  // compute stream around each wait
   uint32_t waits_used = 0;
-  float *send = nullptr, *halo = nullptr;
-  size_t send_floats = 0, halo_floats = 0;
+  float *send = nullptr, *halo = nullptr, *mstage = nullptr;
+  size_t send_floats = 0, halo_floats = 0, mstage_floats = 0;
   uint32_t chunks = 0;  // 0: chosen from the world size when a partition is created
   bool offline = false;  // world > 1 without a communicator: plans can be built, nothing exchanged
   ruvgnn_dist_stats stats = {};
@@ -494,6 +494,7 @@ void ruvgnn_dist_destroy(ruvgnn_dist *d) {
   if (d->comm) nccl()->CommDestroy(d->comm);
   if (d->send) cudaFree(d->send);
   if (d->halo) cudaFree(d->halo);
+  if (d->mstage) cudaFree(d->mstage);
   if (d->ev_ready) cudaEventDestroy(d->ev_ready);
   if (d->ev_x0) cudaEventDestroy(d->ev_x0);
   if (d->ev_x1) cudaEventDestroy(d->ev_x1);
@@ -845,10 +846,15 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
     out_dev = c->out_stage;
   }
   const uint64_t halo_rows = P->dense ? P->n_total : P->n_halo;
+  // Message-row halo for K|V|M layers (dense plane): peers ship M = W_msg x + b only (a third of the
+  // bytes) and K, V are rebuilt where they arrive with the projection's own GEMM (layer.rs:136-137;
+  // the bits of the owner's projection), chunk by chunk between the gather passes.
+  const bool msg_halo = (flags & RUVGNN_DIST_MSG_HALO) && P->dense && !L->r1 && world > 1;
   if (world > 1) {
     if ((rc = ensure_buf(c, &d->halo, &d->halo_floats, (size_t)halo_rows * W + 4))) return rc;
     const uint64_t send_rows = P->dense ? (L->r1 ? 0 : n) : P->n_send;  // message rows go out in place
-    if ((rc = ensure_buf(c, &d->send, &d->send_floats, (size_t)send_rows * W + 4))) return rc;
+    if ((rc = ensure_buf(c, &d->send, &d->send_floats, (size_t)send_rows * (msg_halo ? H : W) + 4))) return rc;
+    if (msg_halo && (rc = ensure_buf(c, &d->mstage, &d->mstage_floats, (size_t)P->n_total * H + 4))) return rc;
   }
   c->timing_valid = c->timing_on;
   if (c->timing_on) {
@@ -896,7 +902,13 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   double bytes_sent = 0, bytes_recv = 0;
   if (world > 1) {
     const float *src = w.halo_src;
-    if (P->dense && !L->r1 && n) {  // K|V|M of every own row, made contiguous
+    const uint32_t Wx = msg_halo ? H : W;  // floats per row on the wire
+    float *land = msg_halo ? d->mstage : d->halo;
+    if (msg_halo && n) {  // message rows of every own row, made contiguous
+      RUVGNN_CUDA_TRY(cudaMemcpy2DAsync(d->send, (size_t)H * 4, w.m, (size_t)w.ldm * 4, (size_t)H * 4, n,
+                                        cudaMemcpyDeviceToDevice, s));
+      src = d->send;
+    } else if (P->dense && !L->r1 && n) {  // K|V|M of every own row, made contiguous
       RUVGNN_CUDA_TRY(cudaMemcpy2DAsync(d->send, (size_t)W * 4, w.halo_src, (size_t)w.ldm * 4,
                                         (size_t)W * 4, n, cudaMemcpyDeviceToDevice, s));
       src = d->send;
@@ -911,12 +923,12 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
       for (uint32_t k = 0; k < n_chunks; ++k) {
         const uint64_t a0 = P->starts[k], a1 = P->starts[k + 1];
         if (a1 > a0)
-          NCCL_TRY(a->AllGather(src + a0 * W, d->halo + (uint64_t)world * a0 * W, (a1 - a0) * W,
+          NCCL_TRY(a->AllGather(src + a0 * Wx, land + (uint64_t)world * a0 * Wx, (a1 - a0) * Wx,
                                 NCCL_FLOAT32, d->comm, cs));
         RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_chunk[k], cs));
       }
-      bytes_sent = (double)n * W * 4 * (world - 1);
-      bytes_recv = (double)(P->n_total - n) * W * 4;
+      bytes_sent = (double)n * Wx * 4 * (world - 1);
+      bytes_recv = (double)(P->n_total - n) * Wx * 4;
     } else {
       NCCL_TRY(a->GroupStart());
       uint64_t soff = 0, roff = 0;
@@ -963,14 +975,37 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
     return RUVGNN_OK;
   };
   d->waits_used = 0;
+  // message-row halo: K | V | M of chunk k's rows, rebuilt from the gathered message rows (own block skipped)
+  auto rebuild_chunk = [&](uint32_t k) -> int32_t {
+    if (!msg_halo) return RUVGNN_OK;
+    const uint64_t a0 = P->starts[k], sz = P->starts[k + 1] - a0;
+    const uint64_t base = (uint64_t)world * a0;
+    const uint64_t lo[2] = {0, (uint64_t)(rank + 1) * sz}, hi[2] = {(uint64_t)rank * sz, (uint64_t)world * sz};
+    for (int part = 0; part < 2; ++part)
+      if (hi[part] > lo[part]) {
+        int32_t r = ruvgnn_layer_expand_halo(c, L, d->mstage + (base + lo[part]) * H, hi[part] - lo[part],
+                                             d->halo + (base + lo[part]) * W);
+        if (r) return r;
+      }
+    return RUVGNN_OK;
+  };
   auto wait_chunk = [&](uint32_t k) -> int32_t {
     const uint32_t i = d->waits_used++;
     RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_w0[i], s));
     RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s, d->ev_chunk[k], 0));
     RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_w1[i], s));
-    return RUVGNN_OK;
+    return rebuild_chunk(k);
   };
 
+  // RUVGNN_COMM_SMS=k: size the grids for k fewer SMs while the exchange is in flight (experiments)
+  static int comm_sms = -1;
+  if (comm_sms < 0) {
+    const char *e = getenv("RUVGNN_COMM_SMS");
+    comm_sms = e ? atoi(e) : 0;
+    if (comm_sms < 0 || comm_sms >= c->sm_count_dev) comm_sms = 0;
+  }
+  const int sm_full = c->sm_count;
+  if (world > 1 && comm_sms > 0) c->sm_count = c->sm_count_dev - comm_sms;
   uint32_t passes = 1;
   if (exact) {
     // all-local row runs first (they need no halo), then everything else after the halo landed
@@ -982,6 +1017,8 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
       for (uint32_t k = 0; k < n_chunks; ++k) RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s, d->ev_chunk[k], 0));
       RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_w1[0], s));
       d->waits_used = 1;
+      for (uint32_t k = 0; k < n_chunks; ++k)
+        if ((rc = rebuild_chunk(k))) return rc;
       for (const auto &r : P->boundary)
         if ((rc = finish_range(r.first, r.second, GatherPass()))) return rc;
     } else if ((rc = finish_range(0, n, GatherPass()))) {
@@ -1003,6 +1040,7 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
       pk.index = (int)k + 1;
       pk.first = false;
       pk.last = k + 1 == n_chunks;
+      if (pk.last) c->sm_count = sm_full;  // the exchange is over
       if (!pk.last) {
         if (n && (rc = gather_rows(c, L, G, d->halo, 0, n, pk, true))) return rc;
       } else if ((rc = finish_range(0, n, pk))) {
@@ -1010,6 +1048,7 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
       }
     }
   }
+  c->sm_count = sm_full;
   if (c->timing_on) cudaEventRecord(c->ev[4], s);
   if (!dev_ptrs) {
     RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_done, c->s_out));

@@ -69,12 +69,18 @@ def main():
         st = d_.last_stats()
         part.forward(layer, xd, od_exact, exact=True)
         ctx.sync()
+        # message-row halo (K, V rebuilt on arrival): the owner's bits, so exact mode stays bit-identical
+        od_m, od_m_exact = torch.empty_like(od), torch.empty_like(od)
+        part.forward(layer, xd, od_m, msg_halo=True)
+        part.forward(layer, xd, od_m_exact, exact=True, msg_halo=True)
+        ctx.sync()
+        msg_ok = bool(torch.equal(od_m_exact, od_exact)) and row_rel(od_m.cpu().numpy(), od_exact.cpu().numpy()) <= 2e-5
         out_host, out_host_exact = np.empty((hi - lo, d), np.float32), np.empty((hi - lo, d), np.float32)
         part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host)
         part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host_exact, exact=True)
         same_host = np.array_equal(out_host, od.cpu().numpy()) and np.array_equal(out_host_exact, od_exact.cpu().numpy())
         gathered = [None] * world
-        dist.all_gather_object(gathered, (od.cpu().numpy(), od_exact.cpu().numpy(), plan_ok, same_host))
+        dist.all_gather_object(gathered, (od.cpu().numpy(), od_exact.cpu().numpy(), plan_ok, same_host and msg_ok))
         if rank == 0:
             from tests.oracle_binding import Oracle
 
@@ -88,7 +94,7 @@ def main():
             print(f"n={n} d={d} heads={heads} mode={mode} locality={loc}: world={world} dense={part.dense} "
                   f"halo_rows={part.n_halo} interior_rows={part.interior_rows} passes={st['passes']} exact_fallback={st['exact']} "
                   f"overlapped: vs oracle {rel_o:.2e}, vs single GPU {rel_s:.2e}; exact bit-identical={bit}; "
-                  f"plan==model {plans}; host variant same {hosts}", flush=True)
+                  f"plan==model {plans}; host + message-halo variants same {hosts}", flush=True)
             ok = ok and rel_o <= 1e-4 and rel_s <= 2e-5 and bit and plans and hosts
         part.close()
     flag = [ok]
