@@ -407,19 +407,16 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
     return blk
 
 
-def secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
-    """The per-GPU slice of config 5: 12.5M nodes x 128 x 4 heads per GPU (100M nodes at N=8), M=32, one layer,
-    range-partitioned with the halo exchange inside the library; locality 0 and 0.9."""
+def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, heads, config, lams=(0.0, 0.9)):
+    """A range-partitioned configuration generated on the device: n nodes x d x heads per GPU, M=32, one layer, halo
+    exchange inside the library; one block per locality value."""
     import ruvector_b200 as rv
     from ruvector_b200 import _lib, dist as rvdist, synth, synth_cuda
 
     torch = h.torch
-    n = a.secondary_nodes or 12_500_000
-    d, heads, m = 128, 4, 32
+    m = 32
     world, rank = h.world, h.rank
     ctx = rv.Context(h.local, h.stream.cuda_stream)
-    dist_ = rvdist.Dist.from_env(ctx)
-    dist_.set_chunks(a.chunks)
     layer = rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d), ctx=ctx)
     slab = 1 << 21
     n_pad = (n + slab - 1) // slab * slab  # feature slabs are addressed by global slab id
@@ -431,7 +428,9 @@ def secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
     R = int(_lib.load().ruvgnn_layer_halo_width(layer._device_layer())) // d
     bounds = rvdist.even_bounds(n * world, world)
     blocks = {}
-    for lam in (0.0, 0.9):
+    for lam in lams:
+        dist_ = rvdist.Dist.from_env(ctx)  # one communicator (and one set of exchange buffers) per graph
+        dist_.set_chunks(a.chunks)
         rp, col, w = synth_cuda.hnsw_like_graph(n, m, seed=0xBEEF + rank, locality=lam, window=a.window,
                                                  n_total=n * world, row_offset=rank * n)
         E = int(col.numel())
@@ -483,12 +482,11 @@ def secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
         blk["roofline"]["note"] = "K-agg time summed over the gather passes; bytes = the single-pass algorithmic bytes"
         blocks[f"locality_{lam}"] = blk
         part.close()
+        dist_.close()
         torch.cuda.empty_cache()
-    res = {"config": "100M nodes d=128, M=32 partitioned over 8xB200 (BASELINE configs[4]): per-GPU slice, weak scaling",
-           "entry": "ruvgnn_dist_forward (device pointers, NCCL inside the library)",
+    res = {"config": config, "entry": "ruvgnn_dist_forward (device pointers, NCCL inside the library)",
            "projection_mode": {0: "fp32_simt", 1: "fp32_3xtf32_tcgen05", 2: "tf32_tcgen05"}[mode], **blocks}
     layer.close()
-    dist_.close()
     del x, out, out2
     ctx.close()
     torch.cuda.empty_cache()
@@ -621,7 +619,20 @@ def main():
             if world == 1:
                 sec = secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src)
             else:
-                sec = secondary_config5_slice(h, a, hbm_peak, peak_src, tf32_peak, tf32_src)
+                # the per-GPU slice of config 5: 12.5M nodes x 128 x 4 heads per GPU (100M nodes at N=8)
+                sec = {"config5_slice": secondary_partitioned(
+                    h, a, hbm_peak, peak_src, tf32_peak, tf32_src, a.secondary_nodes or 12_500_000, 128, 4,
+                    "100M nodes d=128, M=32 partitioned over 8xB200 (BASELINE configs[4]): per-GPU slice, weak scaling")}
+                # config 4: 10M nodes x 768 x 8 heads over the N GPUs (strong: 10M / N per GPU).  At locality 0 every
+                # GPU holds the K|V|M rows of all 10M nodes (92 GB) beside its own: that fits from 8 GPUs on.
+                n4 = 10_000_000 // world
+                if a.secondary_nodes == 0 and world >= 8:
+                    sec["config4"] = secondary_partitioned(
+                        h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n4, 768, 8,
+                        f"10M nodes d=768, 8 heads, M=32, sharded with halo exchange (BASELINE configs[3]): {n4} nodes per GPU")
+                elif a.secondary_nodes == 0:
+                    sec["config4"] = {"skipped": f"10M x 768 at locality 0 needs the K|V|M rows of all 10M nodes per GPU "
+                                                 f"(92 GB) + {n4} own rows x 12 KB: run at 8 GPUs"}
         except rv.GnnError as e:  # reported, never silently dropped
             sec = {"error": f"{type(e).__name__}: {e}"}
         if rank == 0:
