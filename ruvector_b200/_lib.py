@@ -112,10 +112,11 @@ class DistStats(C.Structure):
     """ruvgnn_dist_stats (include/ruvgnn.h)."""
 
     _fields_ = [("bytes_sent", C.c_double), ("bytes_received", C.c_double), ("exposed_wait_ms", C.c_float),
-                ("exchange_ms", C.c_float), ("passes", C.c_uint32), ("exact", C.c_uint32)]
+                ("exchange_ms", C.c_float), ("passes", C.c_uint32), ("exact", C.c_uint32), ("peer_direct", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
-DIST_EXACT, DIST_MSG_HALO = 16, 32
+DIST_EXACT, DIST_MSG_HALO, DIST_NO_PEER_DIRECT = 16, 32, 64
 PART_DEVICE_PTRS, PART_FORCE_SPARSE, PART_FORCE_DENSE = 1, 2, 4
 NCCL_ID_BYTES = 128
 GRAPH_PRENORMALIZED, GRAPH_DEVICE_PTRS, GRAPH_NO_ACTIVE_LIST = 1, 2, 4

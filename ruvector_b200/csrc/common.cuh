@@ -84,6 +84,17 @@ struct GemmArgs {
 cudaError_t launch_gemm_simt(const GemmArgs &a, EpiKind epi, cudaStream_t s, uint64_t *launches);
 
 // ---- gather / aggregate (K-agg) -------------------------------------------
+// Peer-direct plane of the partitioned forward: col_idx holds GLOBAL node ids; a column inside
+// [bounds[rank], bounds[rank+1]) is an own row, any other is read straight from its owner's
+// projected table over NVLink (peer memory mapped with CUDA IPC): the transfer is the gather's own
+// loads, there is no halo buffer and no separate collective to wait for.
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+  const float *base[kMaxPeers] = {};  // peer p's projected table (same layout and row stride as ours)
+  uint64_t bounds[kMaxPeers + 1] = {};
+  int world = 0, rank = 0;
+};
+
 struct GatherArgs {
   const float *P = nullptr;  // [n_local][ldp]: Q | K | V | M (phys order), each H floats
   int64_t ldp = 0;
@@ -106,6 +117,7 @@ struct GatherArgs {
   const uint32_t *seg = nullptr;  // [rows][npass1]
   int npass1 = 0, pass = 0;
   float *ml = nullptr;
+  const PeerTable *peer = nullptr;  // device pointer; non-null: peer-direct plane (col_idx = global ids)
 };
 cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
                           uint64_t *launches);
@@ -134,6 +146,7 @@ struct GatherR1Args {
   const uint32_t *seg = nullptr;
   int npass1 = 0, pass = 0;
   float *ml = nullptr;
+  const PeerTable *peer = nullptr;  // as in GatherArgs
 };
 cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s, uint64_t *launches);
 // Pass-ordered copy of a CSR's edge arrays for the multi-pass gather: pass p = the columns in

@@ -106,6 +106,7 @@ int32_t nccl_fail(const char *what, ncclResult_t r) {
   } while (0)
 
 constexpr int kMaxChunks = 16;
+constexpr size_t kXchgBytes = 128;  // cudaIpcMemHandle_t (64) + ok flag, padded
 
 }  // namespace
 
@@ -122,6 +123,16 @@ struct ruvgnn_dist {
   float *send = nullptr, *halo = nullptr, *mstage = nullptr;
   size_t send_floats = 0, halo_floats = 0, mstage_floats = 0;
   uint32_t chunks = 0;  // 0: chosen from the world size when a partition is created
+  // peer-direct plane: every rank maps its peers' workspaces with CUDA IPC (one process per GPU only)
+  bool ipc_capable = false;
+  struct PeerMap {
+    cudaIpcMemHandle_t handle;
+    void *ptr = nullptr;
+  } peers[kMaxPeers];
+  PeerTable *peer_table_dev = nullptr;
+  unsigned char *xchg_dev = nullptr;  // [world + 1][kXchgBytes]: all-gathered records | own record
+  cudaEvent_t ev_gdone = nullptr, ev_free = nullptr, ev_xchg = nullptr;
+  bool free_pending = false;  // ev_free: every rank has finished reading this rank's table
   bool offline = false;  // world > 1 without a communicator: plans can be built, nothing exchanged
   ruvgnn_dist_stats stats = {};
   bool stats_valid = false;
@@ -134,6 +145,7 @@ struct ruvgnn_partition {
   ruvgnn_graph graph;  // row_ptr / renamed col_idx / edge_w (owned here)
   uint32_t *need_ids = nullptr;  // [n_halo] global ids of the halo slots (sparse plane)
   uint32_t *send_idx = nullptr;  // [n_send] own-local rows to send, grouped by peer
+  uint32_t *col_global = nullptr;  // [n_edges] the caller's global column ids (peer-direct plane)
   std::vector<uint64_t> recv_counts, send_counts;
   bool dense = false;
   std::vector<uint64_t> starts;  // dense plane: row chunk boundaries
@@ -373,6 +385,82 @@ int32_t ensure_buf(ruvgnn_ctx *c, float **buf, size_t *have, size_t need) {
   return RUVGNN_OK;
 }
 
+// All-gather of one kXchgBytes record per rank on the communication stream, read back by the host.
+int32_t exchange_records(ruvgnn_dist *d, const unsigned char *mine, std::vector<unsigned char> *all) {
+  NcclApi *a = nccl();
+  cudaStream_t cs = d->comm_stream;
+  unsigned char *own = d->xchg_dev + (size_t)d->world * kXchgBytes;
+  RUVGNN_CUDA_TRY(cudaMemcpyAsync(own, mine, kXchgBytes, cudaMemcpyHostToDevice, cs));
+  NCCL_TRY(a->AllGather(own, d->xchg_dev, kXchgBytes, NCCL_UINT8, d->comm, cs));
+  all->resize((size_t)d->world * kXchgBytes);
+  RUVGNN_CUDA_TRY(cudaMemcpyAsync(all->data(), d->xchg_dev, all->size(), cudaMemcpyDeviceToHost, cs));
+  RUVGNN_CUDA_TRY(cudaStreamSynchronize(cs));
+  return RUVGNN_OK;
+}
+
+// Maps peer p's allocation (handle from its record) unless that very allocation is already mapped.
+cudaError_t map_peer(ruvgnn_dist *d, int p, const cudaIpcMemHandle_t &h) {
+  ruvgnn_dist::PeerMap &m = d->peers[p];
+  if (m.ptr && memcmp(&m.handle, &h, sizeof h) == 0) return cudaSuccess;
+  if (m.ptr) {
+    cudaIpcCloseMemHandle(m.ptr);
+    m.ptr = nullptr;
+  }
+  cudaError_t e = cudaIpcOpenMemHandle(&m.ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    m.ptr = nullptr;
+    cudaGetLastError();
+    return e;
+  }
+  m.handle = h;
+  return cudaSuccess;
+}
+
+// Collective probe at creation: can every rank map every other rank's device memory?
+int32_t probe_ipc(ruvgnn_dist *d) {
+  d->ipc_capable = false;
+  if (d->world < 2 || d->world > kMaxPeers || !d->comm) return RUVGNN_OK;
+  const char *env = getenv("RUVGNN_PEER_DIRECT");
+  const bool want = !(env && atoi(env) == 0);
+  RUVGNN_CUDA_TRY(cudaMalloc(&d->xchg_dev, (size_t)(d->world + 1) * kXchgBytes));
+  RUVGNN_CUDA_TRY(cudaMalloc(&d->peer_table_dev, sizeof(PeerTable)));
+  void *probe = nullptr;
+  RUVGNN_CUDA_TRY(cudaMalloc(&probe, 4096));
+  unsigned char rec[kXchgBytes] = {};
+  cudaIpcMemHandle_t h;
+  bool ok = want && cudaIpcGetMemHandle(&h, probe) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  if (ok) memcpy(rec, &h, sizeof h);
+  rec[64] = ok ? 1 : 0;
+  std::vector<unsigned char> all;
+  int32_t rc = exchange_records(d, rec, &all);
+  if (rc) {
+    cudaFree(probe);
+    return rc;
+  }
+  for (int p = 0; p < d->world && ok; ++p) {
+    if (!all[(size_t)p * kXchgBytes + 64]) ok = false;
+    if (p == d->rank || !ok) continue;
+    cudaIpcMemHandle_t ph;
+    memcpy(&ph, &all[(size_t)p * kXchgBytes], sizeof ph);
+    void *q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+    } else {
+      cudaIpcCloseMemHandle(q);
+    }
+  }
+  memset(rec, 0, sizeof rec);
+  rec[64] = ok ? 1 : 0;
+  rc = exchange_records(d, rec, &all);  // the verdict must be unanimous (also keeps `probe` alive until all are done)
+  cudaFree(probe);
+  if (rc) return rc;
+  for (int p = 0; p < d->world; ++p) ok = ok && all[(size_t)p * kXchgBytes + 64];
+  d->ipc_capable = ok;
+  return RUVGNN_OK;
+}
+
 // Pass-ordered copy of G's edge arrays for the column bounds given (host, npass + 1 ascending values).
 int32_t build_pass_csr(ruvgnn_ctx *c, const ruvgnn_graph *G, const std::vector<uint64_t> &bounds, PassCsr *out) {
   const int npass = (int)bounds.size() - 1;
@@ -400,6 +488,9 @@ int32_t make_dist(ruvgnn_ctx *ctx, ncclComm_t comm, int rank, int world, ruvgnn_
   RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&d->ev_ready, cudaEventDisableTiming));
   RUVGNN_CUDA_TRY(cudaEventCreate(&d->ev_x0));
   RUVGNN_CUDA_TRY(cudaEventCreate(&d->ev_x1));
+  RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&d->ev_gdone, cudaEventDisableTiming));
+  RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&d->ev_free, cudaEventDisableTiming));
+  RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&d->ev_xchg, cudaEventDisableTiming));
   for (int i = 0; i < kMaxChunks; ++i) {
     RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&d->ev_chunk[i], cudaEventDisableTiming));
     RUVGNN_CUDA_TRY(cudaEventCreate(&d->ev_w0[i]));
@@ -446,6 +537,13 @@ int32_t ruvgnn_dist_create(ruvgnn_ctx *ctx, const uint8_t *id, int32_t rank, int
   int32_t rc = make_dist(ctx, comm, rank, world, out);
   if (rc && comm) nccl()->CommDestroy(comm);
   if (!rc) (*out)->offline = world > 1 && !id;
+  if (!rc && comm) {
+    rc = probe_ipc(*out);
+    if (rc) {
+      ruvgnn_dist_destroy(*out);
+      *out = nullptr;
+    }
+  }
   return rc;
   RUVGNN_ABI_CATCH
 }
@@ -495,6 +593,13 @@ void ruvgnn_dist_destroy(ruvgnn_dist *d) {
   if (d->send) cudaFree(d->send);
   if (d->halo) cudaFree(d->halo);
   if (d->mstage) cudaFree(d->mstage);
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (d->peers[p].ptr) cudaIpcCloseMemHandle(d->peers[p].ptr);
+  if (d->peer_table_dev) cudaFree(d->peer_table_dev);
+  if (d->xchg_dev) cudaFree(d->xchg_dev);
+  if (d->ev_gdone) cudaEventDestroy(d->ev_gdone);
+  if (d->ev_free) cudaEventDestroy(d->ev_free);
+  if (d->ev_xchg) cudaEventDestroy(d->ev_xchg);
   if (d->ev_ready) cudaEventDestroy(d->ev_ready);
   if (d->ev_x0) cudaEventDestroy(d->ev_x0);
   if (d->ev_x1) cudaEventDestroy(d->ev_x1);
@@ -534,6 +639,7 @@ void ruvgnn_partition_destroy(ruvgnn_partition *p) {
   if (p->graph.edge_w) cudaFree(p->graph.edge_w);
   if (p->need_ids) cudaFree(p->need_ids);
   if (p->send_idx) cudaFree(p->send_idx);
+  if (p->col_global) cudaFree(p->col_global);
   if (p->pass.col) cudaFree(p->pass.col);
   if (p->pass.w) cudaFree(p->pass.w);
   if (p->pass.seg) cudaFree(p->pass.seg);
@@ -597,6 +703,10 @@ int32_t ruvgnn_partition_create(ruvgnn_dist *d, const uint64_t *bounds, const ui
     return fail(RUVGNN_ERR_INVALID_INPUT, (flag & 1) ? "row_ptr is not monotone non-decreasing"
                                                      : "column id outside the global node range");
 
+  if (world > 1 && !d->offline && E) {  // kept for the peer-direct plane
+    RUVGNN_CUDA_TRY(cudaMalloc(&P->col_global, (E + 4) * sizeof(uint32_t)));
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(P->col_global, G.col_idx, E * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  }
   // ---- de-duplicate the remote columns: bitmap + prefix popcount --------------------------
   const uint64_t n_words = (n_total + 63) / 64 + 1;
   const uint64_t n_blocks = (n_words + 1023) / 1024;
@@ -834,8 +944,18 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   int32_t rc;
   if (dev_ptrs && x == out) return fail(RUVGNN_ERR_INVALID_INPUT, "out must not alias x (Jacobi update)");
 
+  // Peer-direct plane: when the plan is sparse (few remote neighbours per row) the gather reads the
+  // remote rows straight from their owners' tables over NVLink -- single pass, stored order, so the
+  // bits of the single-GPU run -- instead of packing, exchanging and re-reading a halo buffer.
+  const bool direct = world > 1 && d->ipc_capable && !P->dense && P->col_global && mp_ok &&
+                      !(flags & RUVGNN_DIST_NO_PEER_DIRECT);
+  if (direct && d->free_pending) {  // peers may still be reading the table the projection overwrites
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s, d->ev_free, 0));
+    d->free_pending = false;
+  }
   // ---- buffers --------------------------------------------------------------------------------
-  c->state_per_node = !exact;
+  c->state_per_node = !exact && !direct;
+  c->peer_dev = nullptr;
   if ((rc = ensure_ws(c, L, n))) return rc;
   const float *x_dev = x;
   float *out_dev = out;
@@ -845,12 +965,12 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
     x_dev = c->x_stage;
     out_dev = c->out_stage;
   }
-  const uint64_t halo_rows = P->dense ? P->n_total : P->n_halo;
+  const uint64_t halo_rows = direct ? 0 : (P->dense ? P->n_total : P->n_halo);
   // Message-row halo for K|V|M layers (dense plane): peers ship M = W_msg x + b only (a third of the
   // bytes) and K, V are rebuilt where they arrive with the projection's own GEMM (layer.rs:136-137;
   // the bits of the owner's projection), chunk by chunk between the gather passes.
   const bool msg_halo = (flags & RUVGNN_DIST_MSG_HALO) && P->dense && !L->r1 && world > 1;
-  if (world > 1) {
+  if (world > 1 && !direct) {
     if ((rc = ensure_buf(c, &d->halo, &d->halo_floats, (size_t)halo_rows * W + 4))) return rc;
     const uint64_t send_rows = P->dense ? (L->r1 ? 0 : n) : P->n_send;  // message rows go out in place
     if ((rc = ensure_buf(c, &d->send, &d->send_floats, (size_t)send_rows * (msg_halo ? H : W) + 4))) return rc;
@@ -865,7 +985,7 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   // ---- project (host buffers: row blocks are projected as their H2D copies land) --------------
   // Message-row halos leave as soon as the message GEMM is done; the query GEMM runs beside the
   // exchange.  K|V|M halos need the whole projection.
-  const bool early = L->r1 && world > 1 && dev_ptrs;
+  const bool early = L->r1 && world > 1 && dev_ptrs && !direct;
   if (dev_ptrs) {
     if (c->timing_on) cudaEventRecord(c->ev[1], s);
     if ((rc = do_project_rows(c, L, n, x_dev, 0, n, early ? 1 : 3))) return rc;
@@ -898,9 +1018,45 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   Ws w = carve(c, L, n);
 
   // ---- exchange, on the communication stream --------------------------------------------------
-  const uint32_t n_chunks = world == 1 ? 0 : (P->dense ? (uint32_t)(P->starts.size() - 1) : 1);
+  const uint32_t n_chunks = (world == 1 || direct) ? 0 : (P->dense ? (uint32_t)(P->starts.size() - 1) : 1);
   double bytes_sent = 0, bytes_recv = 0;
-  if (world > 1) {
+  if (direct) {
+    // every rank publishes the IPC handle of its workspace (the projected table sits at its start);
+    // the all-gather is also the barrier "every rank has finished projecting"
+    RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_ready, s));
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_ready, 0));
+    RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_x0, cs));
+    unsigned char rec[kXchgBytes] = {};
+    cudaIpcMemHandle_t h;
+    RUVGNN_CUDA_TRY(cudaIpcGetMemHandle(&h, c->ws));
+    memcpy(rec, &h, sizeof h);
+    rec[64] = 1;
+    std::vector<unsigned char> all;
+    if ((rc = exchange_records(d, rec, &all))) return rc;
+    PeerTable t;
+    t.world = world;
+    t.rank = rank;
+    for (int p = 0; p <= world; ++p) t.bounds[p] = P->bounds[p];
+    for (int p = 0; p < world; ++p) {
+      if (p == rank) {
+        t.base[p] = c->ws;
+        continue;
+      }
+      cudaIpcMemHandle_t ph;
+      memcpy(&ph, &all[(size_t)p * kXchgBytes], sizeof ph);
+      cudaError_t e = map_peer(d, p, ph);
+      if (e != cudaSuccess)
+        return fail(RUVGNN_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer workspace): ") + cudaGetErrorString(e));
+      t.base[p] = static_cast<const float *>(d->peers[p].ptr);
+    }
+    RUVGNN_CUDA_TRY(cudaMemcpyAsync(d->peer_table_dev, &t, sizeof t, cudaMemcpyHostToDevice, cs));
+    RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_x1, cs));
+    RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_xchg, cs));
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s, d->ev_xchg, 0));
+    c->peer_dev = d->peer_table_dev;
+    c->peer_cols = P->col_global;
+    bytes_recv = (double)P->remote_edges * W * 4;  // pulled by the gather's own loads, no de-duplication
+  } else if (world > 1) {
     const float *src = w.halo_src;
     const uint32_t Wx = msg_halo ? H : W;  // floats per row on the wire
     float *land = msg_halo ? d->mstage : d->halo;
@@ -1007,7 +1163,17 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   const int sm_full = c->sm_count;
   if (world > 1 && comm_sms > 0) c->sm_count = c->sm_count_dev - comm_sms;
   uint32_t passes = 1;
-  if (exact) {
+  if (direct) {
+    if ((rc = finish_range(0, n, GatherPass()))) return rc;
+    c->peer_dev = nullptr;
+    // "every rank has finished reading": a tiny all-gather on the communication stream; the next
+    // forward's projection (which overwrites the table) waits for it
+    RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_gdone, s));
+    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_gdone, 0));
+    NCCL_TRY(a->AllGather(d->xchg_dev + (size_t)world * kXchgBytes, d->xchg_dev, 1, NCCL_UINT8, d->comm, cs));
+    RUVGNN_CUDA_TRY(cudaEventRecord(d->ev_free, cs));
+    d->free_pending = true;
+  } else if (exact) {
     // all-local row runs first (they need no halo), then everything else after the halo landed
     if (world > 1)
       for (const auto &r : P->interior)
@@ -1059,7 +1225,8 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   d->stats.bytes_sent = bytes_sent;
   d->stats.bytes_received = bytes_recv;
   d->stats.passes = passes;
-  d->stats.exact = exact ? 1 : 0;
+  d->stats.exact = (exact || direct) ? 1 : 0;
+  d->stats.peer_direct = direct ? 1 : 0;
   d->stats_valid = true;
   if (!(flags & RUVGNN_FWD_ASYNC) || !dev_ptrs) RUVGNN_CUDA_TRY(cudaStreamSynchronize(s));
   if (d->comm) {

@@ -55,6 +55,9 @@ struct ruvgnn_ctx {
   // multi-pass gather (dist.cu): keep the gather state o|agg (or S_g|agg) and the running softmax
   // (max, sum) of every node between passes instead of one row block
   bool state_per_node = false;
+  // peer-direct plane (dist.cu): the gather reads remote rows from the peers' tables; col_idx = global ids
+  const ruvgnn::PeerTable *peer_dev = nullptr;
+  const uint32_t *peer_cols = nullptr;
 };
 
 struct ruvgnn_layer {

@@ -283,6 +283,10 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
     ga.first = pass.first ? 1 : 0;
     ga.last = pass.last ? 1 : 0;
     ga.ml = w.ML;
+    if (c->peer_dev && !pass.csr) {
+      ga.peer = c->peer_dev;
+      ga.col_idx = c->peer_cols;
+    }
     RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
   } else {
     GatherR1Args ga;
@@ -311,6 +315,10 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
     ga.first = pass.first ? 1 : 0;
     ga.last = pass.last ? 1 : 0;
     ga.ml = w.ML;
+    if (c->peer_dev && !pass.csr) {
+      ga.peer = c->peer_dev;
+      ga.col_idx = c->peer_cols;
+    }
     RUVGNN_CUDA_TRY(launch_gather_r1(ga, c->sm_count, c->stream, &c->launches));
   }
   if (agg_end) {
@@ -1132,6 +1140,7 @@ int32_t ruvgnn_layer_forward(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_
   const bool dev_ptrs = flags & RUVGNN_FWD_DEVICE_PTRS;
   const bool timing = flags & RUVGNN_FWD_TIMING;
   c->state_per_node = false;
+  c->peer_dev = nullptr;
   const float *x_dev = x;
   float *out_dev = out;
   int32_t rc;
@@ -1237,6 +1246,7 @@ int32_t ruvgnn_stack_forward(ruvgnn_ctx *c, const ruvgnn_layer *const *layers,
   const bool timing = flags & RUVGNN_FWD_TIMING;
   c->timing_valid = false;
   c->state_per_node = false;
+  c->peer_dev = nullptr;
   int32_t rc;
   size_t ws_need = 0;
   for (uint32_t l = 0; l < n_layers; ++l) {
@@ -1338,6 +1348,7 @@ int32_t ruvgnn_layer_project(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t n_lo
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = c->timing_on;
   c->state_per_node = false;
+  c->peer_dev = nullptr;
   if (c->timing_on) {
     begin_timing_slot(c);
     cudaEventRecord(c->ev[0], c->stream);
@@ -1359,6 +1370,7 @@ int32_t ruvgnn_layer_project_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, uint64_t
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = c->timing_on;
   c->state_per_node = false;
+  c->peer_dev = nullptr;
   if (c->timing_on && row_begin == 0) {
     begin_timing_slot(c);
     cudaEventRecord(c->ev[0], c->stream);
@@ -1595,6 +1607,7 @@ extern "C" int32_t ruvgnn_hierarchical_forward(ruvgnn_ctx *c, const float *queri
   if (!dg.ok) return fail(RUVGNN_ERR_CUDA, "cudaSetDevice failed");
   c->timing_valid = false;
   c->state_per_node = false;
+  c->peer_dev = nullptr;
   const uint64_t nq = n_queries;
   DevBuf cur, nxt;
   RUVGNN_CUDA_TRY(cur.alloc(nq * query_dim * sizeof(float)));

@@ -52,16 +52,29 @@ __device__ __forceinline__ WeightRule make_rule(const float *edge_w, uint64_t be
   return r;
 }
 
+// Peer-direct addressing: the row of global node g inside its owner's table (row stride ld floats).
+__device__ __forceinline__ const float *peer_row(const PeerTable &t, uint64_t g, int64_t ld) {
+  int o = 0;
+  while (o + 1 < t.world && g >= t.bounds[o + 1]) ++o;
+  return t.base[o] + (g - t.bounds[o]) * (uint64_t)ld;
+}
+
 template <int P>
 struct RowRegs {
   float4 k[P], v[P], m[P];
 };
 
 // P = H/128 float4 per lane per row; LH = 32/heads lanes per head; U = edges in flight.
-template <int P, int LH, int U>
+template <int P, int LH, int U, bool PEER>
 __global__ void __launch_bounds__(128) gather_fast_kernel(GatherArgs a, float inv_scale) {
   constexpr int H = 128 * P;
   constexpr int V = 32 * P;  // float4 per H-row
+  __shared__ PeerTable s_peer;
+  if (PEER) {
+    if (threadIdx.x == 0) s_peer = *a.peer;
+    __syncthreads();
+  }
+  const uint64_t own_lo = PEER ? s_peer.bounds[s_peer.rank] : 0;
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -87,6 +100,11 @@ __global__ void __launch_bounds__(128) gather_fast_kernel(GatherArgs a, float in
     float mx = -INFINITY, l = 0.f;
 
     auto row_of = [&](uint32_t col) -> const float4 * {
+      if (PEER) {
+        const uint64_t l = (uint64_t)col - own_lo;  // own row when inside [lo, hi)
+        return l < a.n_local ? reinterpret_cast<const float4 *>(a.P + l * a.ldp + H)
+                             : reinterpret_cast<const float4 *>(peer_row(s_peer, col, a.ldp) + H);
+      }
       return (uint64_t)col < a.n_local
                  ? reinterpret_cast<const float4 *>(a.P + (uint64_t)col * a.ldp + H)
                  : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * (3 * H));
@@ -600,9 +618,24 @@ __device__ __forceinline__ float reduce_scatter_xor(float (&v)[N]) {
 // Register budget: 16 resident warps per SM (128 registers).  Measured at 4M nodes: cutting it for 20 / 24
 // warps (96 / 80 registers, small spills) is slower (24.8 / 28.3 vs 23.8 ms), and so is requesting the
 // next step's rows one step ahead (167 registers, 12 warps: 26.6 ms).
-template <int HEADS, bool HALO, bool PREFETCH>
+template <int HEADS, int HALO, bool PREFETCH>  // HALO: 0 own rows only, 1 halo buffer, 2 peer-direct
 __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args a, float scale_log2) {
   constexpr int H = 128, EB = 8, N = EB * HEADS, REP = 32 / N;
+  __shared__ PeerTable s_peer;
+  if (HALO == 2) {
+    if (threadIdx.x == 0) s_peer = *a.peer;
+    __syncwarp();
+  }
+  const uint64_t own_lo = HALO == 2 ? s_peer.bounds[s_peer.rank] : 0;
+  // the message row of column `col`
+  auto mrow = [&](uint32_t col) -> const float * {
+    if (HALO == 2) {
+      const uint64_t l = (uint64_t)col - own_lo;
+      return l < a.n_local ? a.M + l * a.ldm : peer_row(s_peer, col, a.ldm);
+    }
+    if (HALO == 1 && (uint64_t)col >= a.n_local) return a.halo + ((uint64_t)col - a.n_local) * H;
+    return a.M + (uint64_t)col * a.ldm;
+  };
   // ONE warp per block: the node, its row bounds and every loop trip count then derive from
   // blockIdx, which the compiler knows to be warp-uniform -- the shuffles compile to bare SHFL
   // (with 4 warps per block each one sat in a WARPSYNC / ENDCOLLECTIVE region).
@@ -643,9 +676,7 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args 
           // line L % 4 of the row of edge jj + 8 + L / 4, so those loads find their data on chip
           const int nsrc = jj + EB + my_slot;
           const uint32_t ncol = __shfl_sync(0xffffffffu, my_col, nsrc < cnt ? nsrc : cnt - 1);
-          const float *nrow = (HALO && (uint64_t)ncol >= a.n_local)
-                                  ? a.halo + ((uint64_t)ncol - a.n_local) * H
-                                  : a.M + (uint64_t)ncol * a.ldm;
+          const float *nrow = mrow(ncol);
           asm volatile("prefetch.global.L1 [%0];" ::"l"(nrow + (lane & 3) * 32));
         }
 #pragma unroll
@@ -653,14 +684,7 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args 
           // slots beyond the row re-read its last edge (score masked below, weight 0)
           const int src = jj + (u ^ my_slot);
           const uint32_t col = __shfl_sync(0xffffffffu, my_col, src < cnt ? src : cnt - 1);
-          const float4 *row;
-          if (HALO)
-            row = (uint64_t)col < a.n_local
-                      ? reinterpret_cast<const float4 *>(a.M + (uint64_t)col * a.ldm)
-                      : reinterpret_cast<const float4 *>(a.halo + ((uint64_t)col - a.n_local) * H);
-          else
-            row = reinterpret_cast<const float4 *>(a.M + (uint64_t)col * a.ldm);
-          r[u] = ldg4(row + lane);
+          r[u] = ldg4(reinterpret_cast<const float4 *>(mrow(col)) + lane);
         }
         float s[N];  // position u * HEADS + g holds the partial of edge slot u ^ my_slot, head g ^ my_head
 #pragma unroll
@@ -874,15 +898,18 @@ cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, c
         const char *e = getenv("RUVGNN_R1_PF");
         pf = (e && atoi(e) == 0) ? 0 : 1;
       }
-      if (a.halo)
-        gather_r1_batched_kernel<HEADS, true, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+      if (a.peer)
+        gather_r1_batched_kernel<HEADS, 2, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+      else if (a.halo)
+        gather_r1_batched_kernel<HEADS, 1, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
       else if (pf)
-        gather_r1_batched_kernel<HEADS, false, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+        gather_r1_batched_kernel<HEADS, 0, true><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
       else
-        gather_r1_batched_kernel<HEADS, false, false><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
+        gather_r1_batched_kernel<HEADS, 0, false><<<(unsigned)warps, 32, 0, s>>>(a, scale_log2);
       return cudaGetLastError();
     }
   }
+  if (a.peer) return cudaErrorNotSupported;
   gather_r1_kernel<HEADS, (HEADS <= 4 ? 8 : 4)><<<(unsigned)blocks, 32 * wpb, 0, s>>>(a, scale_log2);
   return cudaGetLastError();
 }
@@ -909,13 +936,25 @@ cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cu
     }
     return cudaGetLastError();
   }
+  if (a.peer) {
+    switch (32 / a.heads) {
+      case 32: gather_fast_kernel<P, 32, U, true><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 16: gather_fast_kernel<P, 16, U, true><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 8: gather_fast_kernel<P, 8, U, true><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 4: gather_fast_kernel<P, 4, U, true><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 2: gather_fast_kernel<P, 2, U, true><<<grid, block, 0, s>>>(a, inv_scale); break;
+      case 1: gather_fast_kernel<P, 1, U, true><<<grid, block, 0, s>>>(a, inv_scale); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
   switch (32 / a.heads) {
-    case 32: gather_fast_kernel<P, 32, U><<<grid, block, 0, s>>>(a, inv_scale); break;
-    case 16: gather_fast_kernel<P, 16, U><<<grid, block, 0, s>>>(a, inv_scale); break;
-    case 8: gather_fast_kernel<P, 8, U><<<grid, block, 0, s>>>(a, inv_scale); break;
-    case 4: gather_fast_kernel<P, 4, U><<<grid, block, 0, s>>>(a, inv_scale); break;
-    case 2: gather_fast_kernel<P, 2, U><<<grid, block, 0, s>>>(a, inv_scale); break;
-    case 1: gather_fast_kernel<P, 1, U><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 32: gather_fast_kernel<P, 32, U, false><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 16: gather_fast_kernel<P, 16, U, false><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 8: gather_fast_kernel<P, 8, U, false><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 4: gather_fast_kernel<P, 4, U, false><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 2: gather_fast_kernel<P, 2, U, false><<<grid, block, 0, s>>>(a, inv_scale); break;
+    case 1: gather_fast_kernel<P, 1, U, false><<<grid, block, 0, s>>>(a, inv_scale); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -966,7 +1005,7 @@ cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStre
       default: return cudaErrorInvalidValue;
     }
   }
-  if (a.multipass) return cudaErrorNotSupported;  // generic layouts: single-pass only
+  if (a.multipass || a.peer) return cudaErrorNotSupported;  // generic layouts: single-pass, halo buffer only
   const size_t per_warp = (size_t)(3 * a.H + 2 * a.heads) * sizeof(float);
   int wpb = (int)((size_t)(96 * 1024) / per_warp);
   if (wpb > 4) wpb = 4;

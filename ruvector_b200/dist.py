@@ -344,7 +344,8 @@ class Partition:
             rc.ctypes.data_as(u64), sc.ctypes.data_as(u64)))
         return {"col_idx": col, "need_ids": need, "send_idx": send, "recv_counts": rc, "send_counts": sc}
 
-    def forward(self, layer, x_dev, out_dev, exact: bool = False, asynchronous: bool = True, msg_halo: bool = False):
+    def forward(self, layer, x_dev, out_dev, exact: bool = False, asynchronous: bool = True, msg_halo: bool = False,
+                peer_direct: bool = True):
         """Device buffers (objects with ``data_ptr()`` or raw pointers); enqueue only by default.
         The work runs on the ctx stream (``ruvgnn_ctx_stream``): order the buffers against it."""
         import ctypes as C
@@ -354,11 +355,12 @@ class Partition:
         xp = x_dev.data_ptr() if hasattr(x_dev, "data_ptr") else int(x_dev)
         op = out_dev.data_ptr() if hasattr(out_dev, "data_ptr") else int(out_dev)
         flags = (_lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.DIST_EXACT if exact else 0)
-                 | (_lib.DIST_MSG_HALO if msg_halo else 0))
+                 | (_lib.DIST_MSG_HALO if msg_halo else 0) | (0 if peer_direct else _lib.DIST_NO_PEER_DIRECT))
         _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
                                                  C.c_void_p(xp), C.c_void_p(op), flags))
 
-    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray, exact: bool = False, msg_halo: bool = False):
+    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray, exact: bool = False, msg_halo: bool = False,
+                     peer_direct: bool = True):
         """Host buffers in, host buffers out (H2D / D2H inside the call, pipelined in row blocks when the
         buffers are pinned): the e2e leg of bench.py.  Blocks until the output is there."""
         import ctypes as C
@@ -371,7 +373,8 @@ class Partition:
             raise ValueError("x must be [n_local, input_dim] and out [n_local, hidden_dim]")
         _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
                                                  C.c_void_p(x_np.ctypes.data), C.c_void_p(out_np.ctypes.data),
-                                                 (_lib.DIST_EXACT if exact else 0) | (_lib.DIST_MSG_HALO if msg_halo else 0)))
+                                                 (_lib.DIST_EXACT if exact else 0) | (_lib.DIST_MSG_HALO if msg_halo else 0)
+                                                 | (0 if peer_direct else _lib.DIST_NO_PEER_DIRECT)))
 
     def close(self):
         if getattr(self, "handle", None):
