@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--window", type=int, default=4096, help="id window of the local neighbours (with --locality)")
     ap.add_argument("--exact", action="store_true", help="N>1: single-pass gather after the halo landed (bit-identical to 1 GPU)")
     ap.add_argument("--chunks", type=int, default=0, help="N>1: row chunks of the dense plane (0: the library's choice from the world size)")
+    ap.add_argument("--plane", default=None, choices=["sparse", "dense"], help="N>1: force the halo plan's data plane")
     ap.add_argument("--no-peer-direct", action="store_true", help="N>1, sparse plans: pack + all-to-all-v instead of peer-direct reads")
     ap.add_argument("--msg-halo", action="store_true", help="N>1, K|V|M layers: ship message rows and rebuild K, V on arrival")
     ap.add_argument("--mode", type=int, default=-1, help="-1: the library default (tcgen05 3xTF32 where the shape allows)")
@@ -439,7 +440,7 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
                                                  n_total=n * world, row_offset=rank * n)
         E = int(col.numel())
         t0 = time.perf_counter()
-        part = rvdist.Partition(dist_, bounds, rp, col, w, device_ptrs=True)
+        part = rvdist.Partition(dist_, bounds, rp, col, w, device_ptrs=True, plane=a.plane)
         torch.cuda.synchronize()
         plan_s = time.perf_counter() - t0
         del rp, col, w
@@ -524,7 +525,7 @@ def main():
 
             dist_ = rvdist.Dist.from_env(ctx)
             dist_.set_chunks(a.chunks)
-            part = rvdist.Partition.from_graph(dist_, g, a.nodes)
+            part = rvdist.Partition.from_graph(dist_, g, a.nodes, plane=a.plane)
             step_fn = lambda xd, od: part.forward(layer, xd, od, exact=a.exact, msg_halo=a.msg_halo, peer_direct=not a.no_peer_direct)
             dg = None
         else:
