@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--exact", action="store_true", help="N>1: single-pass gather after the halo landed (bit-identical to 1 GPU)")
     ap.add_argument("--chunks", type=int, default=0, help="N>1: row chunks of the dense plane (0: the library's choice from the world size)")
     ap.add_argument("--plane", default=None, choices=["sparse", "dense"], help="N>1: force the halo plan's data plane")
-    ap.add_argument("--no-peer-direct", action="store_true", help="N>1, sparse plans: pack + all-to-all-v instead of peer-direct reads")
+    ap.add_argument("--peer-direct", action="store_true", help="N>1, sparse plans: the gather reads remote rows from the peers' tables over NVLink")
     ap.add_argument("--msg-halo", action="store_true", help="N>1, K|V|M layers: ship message rows and rebuild K, V on arrival")
     ap.add_argument("--mode", type=int, default=-1, help="-1: the library default (tcgen05 3xTF32 where the shape allows)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -446,11 +446,11 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
         del rp, col, w
         torch.cuda.empty_cache()
         steps, warmup = max(2, min(a.steps, 5)), 3
-        ms = h.timed(lambda: part.forward(layer, x, out, exact=a.exact, peer_direct=not a.no_peer_direct), steps, warmup)
+        ms = h.timed(lambda: part.forward(layer, x, out, exact=a.exact, peer_direct=a.peer_direct), steps, warmup)
         stats = dist_.last_stats()
         ctx.set_timing(True)
         for _ in range(2):
-            part.forward(layer, x, out, exact=a.exact, peer_direct=not a.no_peer_direct)
+            part.forward(layer, x, out, exact=a.exact, peer_direct=a.peer_direct)
         t = ctx.last_timing()
         ctx.set_timing(False)
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
@@ -465,7 +465,7 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
             if out2 is None:
                 out2 = torch.empty_like(out)
             part.forward(layer, x, out2, exact=True, asynchronous=False, peer_direct=False)
-            part.forward(layer, x, out, asynchronous=False, peer_direct=not a.no_peer_direct)
+            part.forward(layer, x, out, asynchronous=False, peer_direct=a.peer_direct)
             sl = slice(0, n, max(n // 65536, 1))
             num = (out[sl] - out2[sl]).norm(dim=1)
             den = out2[sl].norm(dim=1).clamp_min(1e-6)
@@ -526,7 +526,7 @@ def main():
             dist_ = rvdist.Dist.from_env(ctx)
             dist_.set_chunks(a.chunks)
             part = rvdist.Partition.from_graph(dist_, g, a.nodes, plane=a.plane)
-            step_fn = lambda xd, od: part.forward(layer, xd, od, exact=a.exact, msg_halo=a.msg_halo, peer_direct=not a.no_peer_direct)
+            step_fn = lambda xd, od: part.forward(layer, xd, od, exact=a.exact, msg_halo=a.msg_halo, peer_direct=a.peer_direct)
             dg = None
         else:
             dg = g.to_device(ctx)
@@ -570,7 +570,7 @@ def main():
             out_pin = torch.empty(n, H, dtype=torch.float32).pin_memory()
             x_np, out_np = x_pin.numpy(), out_pin.numpy()
             if world > 1:
-                e2e_fn = lambda: part.forward_host(layer, x_np, out_np, exact=a.exact, msg_halo=a.msg_halo, peer_direct=not a.no_peer_direct)
+                e2e_fn = lambda: part.forward_host(layer, x_np, out_np, exact=a.exact, msg_halo=a.msg_halo, peer_direct=a.peer_direct)
             else:
                 e2e_fn = lambda: layer.forward_graph(x_np, dg, out=out_np)
             k2 = max(2, min(a.steps, 5))

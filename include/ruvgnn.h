@@ -390,19 +390,19 @@ int32_t ruvgnn_partition_download(const ruvgnn_partition *p, uint32_t *col_idx_l
  *   RUVGNN_DIST_EXACT   single-pass gather after the whole halo has arrived, all-local row runs
  *               first: every row goes through exactly the arithmetic of the single-GPU run
  *               (bit-identical outputs).
- *   peer-direct (automatic)   sparse plans, one process per GPU: the ranks map each other's projected
- *               tables with CUDA IPC and the gather kernel reads the remote rows itself over NVLink
- *               -- no pack, no halo buffer, no collective on the data path; single pass in stored
- *               order, so the outputs are bit-identical to the single-GPU run.  Two 128-byte
- *               all-gathers per layer are the only synchronisation (tables ready / tables free).
- *               RUVGNN_DIST_NO_PEER_DIRECT (or a host where IPC mapping fails, probed collectively
- *               at ruvgnn_dist_create) keeps the pack + all-to-all-v path.
+ *   RUVGNN_DIST_PEER_DIRECT   sparse plans, one process per GPU: the ranks map each other's
+ *               projected tables with CUDA IPC (probed collectively at ruvgnn_dist_create) and the gather
+ *               kernel reads the remote rows itself over NVLink -- no pack, no halo buffer, no collective
+ *               on the data path; single pass in stored order, so the outputs are bit-identical to the
+ *               single-GPU run.  Two 128-byte all-gathers per layer are the only synchronisation (tables
+ *               ready / tables free).  Opt-in: the reads are not de-duplicated, so it pays only when few
+ *               remote rows are referenced more than once per rank.  Ignored where IPC mapping failed.
  *   RUVGNN_DIST_MSG_HALO   dense plane, K|V|M layers: peers ship the message rows only (a third of
  *               the bytes) and K, V are rebuilt on arrival with the projection's own GEMM
  *               (layer.rs:136-137), so a rebuilt row carries the owner's bits; ignored elsewhere. */
 #define RUVGNN_DIST_EXACT 16u
 #define RUVGNN_DIST_MSG_HALO 32u
-#define RUVGNN_DIST_NO_PEER_DIRECT 64u
+#define RUVGNN_DIST_PEER_DIRECT 64u
 int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *p, const ruvgnn_layer *layer,
                             const float *x, float *out, uint32_t flags);
 typedef struct {

@@ -944,11 +944,14 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   int32_t rc;
   if (dev_ptrs && x == out) return fail(RUVGNN_ERR_INVALID_INPUT, "out must not alias x (Jacobi update)");
 
-  // Peer-direct plane: when the plan is sparse (few remote neighbours per row) the gather reads the
-  // remote rows straight from their owners' tables over NVLink -- single pass, stored order, so the
-  // bits of the single-GPU run -- instead of packing, exchanging and re-reading a halo buffer.
+  // Peer-direct plane (opt-in, RUVGNN_DIST_PEER_DIRECT): on a sparse plan the gather reads the remote
+  // rows straight from their owners' tables over NVLink -- single pass, stored order, so the bits of
+  // the single-GPU run -- instead of packing, exchanging and re-reading a halo buffer.  Measured
+  // (2 B200s, config-2 shape, 5% remote edges): the NVLink reads run at ~700 GB/s but add to the gather
+  // time instead of hiding under it, and they are not de-duplicated, so the pack + all-to-all-v path
+  // wins whenever a remote row is referenced more than once or twice per rank.
   const bool direct = world > 1 && d->ipc_capable && !P->dense && P->col_global && mp_ok &&
-                      !(flags & RUVGNN_DIST_NO_PEER_DIRECT);
+                      (flags & RUVGNN_DIST_PEER_DIRECT);
   if (direct && d->free_pending) {  // peers may still be reading the table the projection overwrites
     RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s, d->ev_free, 0));
     d->free_pending = false;

@@ -676,8 +676,12 @@ __global__ void __launch_bounds__(32, 16) gather_r1_batched_kernel(GatherR1Args 
           // line L % 4 of the row of edge jj + 8 + L / 4, so those loads find their data on chip
           const int nsrc = jj + EB + my_slot;
           const uint32_t ncol = __shfl_sync(0xffffffffu, my_col, nsrc < cnt ? nsrc : cnt - 1);
-          const float *nrow = mrow(ncol);
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(nrow + (lane & 3) * 32));
+          // own rows only: an L1 prefetch of a peer address is pathologically slow (measured: 30M remote
+          // message rows took 1.9 s with it)
+          if (HALO != 2 || (uint64_t)ncol - own_lo < a.n_local) {
+            const float *nrow = mrow(ncol);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nrow + (lane & 3) * 32));
+          }
         }
 #pragma unroll
         for (int u = 0; u < EB; ++u) {

@@ -345,7 +345,7 @@ class Partition:
         return {"col_idx": col, "need_ids": need, "send_idx": send, "recv_counts": rc, "send_counts": sc}
 
     def forward(self, layer, x_dev, out_dev, exact: bool = False, asynchronous: bool = True, msg_halo: bool = False,
-                peer_direct: bool = True):
+                peer_direct: bool = False):
         """Device buffers (objects with ``data_ptr()`` or raw pointers); enqueue only by default.
         The work runs on the ctx stream (``ruvgnn_ctx_stream``): order the buffers against it."""
         import ctypes as C
@@ -355,12 +355,12 @@ class Partition:
         xp = x_dev.data_ptr() if hasattr(x_dev, "data_ptr") else int(x_dev)
         op = out_dev.data_ptr() if hasattr(out_dev, "data_ptr") else int(out_dev)
         flags = (_lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.DIST_EXACT if exact else 0)
-                 | (_lib.DIST_MSG_HALO if msg_halo else 0) | (0 if peer_direct else _lib.DIST_NO_PEER_DIRECT))
+                 | (_lib.DIST_MSG_HALO if msg_halo else 0) | (_lib.DIST_PEER_DIRECT if peer_direct else 0))
         _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
                                                  C.c_void_p(xp), C.c_void_p(op), flags))
 
     def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray, exact: bool = False, msg_halo: bool = False,
-                     peer_direct: bool = True):
+                     peer_direct: bool = False):
         """Host buffers in, host buffers out (H2D / D2H inside the call, pipelined in row blocks when the
         buffers are pinned): the e2e leg of bench.py.  Blocks until the output is there."""
         import ctypes as C
@@ -374,7 +374,7 @@ class Partition:
         _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
                                                  C.c_void_p(x_np.ctypes.data), C.c_void_p(out_np.ctypes.data),
                                                  (_lib.DIST_EXACT if exact else 0) | (_lib.DIST_MSG_HALO if msg_halo else 0)
-                                                 | (0 if peer_direct else _lib.DIST_NO_PEER_DIRECT)))
+                                                 | (_lib.DIST_PEER_DIRECT if peer_direct else 0)))
 
     def close(self):
         if getattr(self, "handle", None):

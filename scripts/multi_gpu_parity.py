@@ -75,15 +75,15 @@ def main():
         part.forward(layer, xd, od_m_exact, exact=True, msg_halo=True)
         ctx.sync()
         msg_ok = bool(torch.equal(od_m_exact, od_exact)) and row_rel(od_m.cpu().numpy(), od_exact.cpu().numpy()) <= 2e-5
-        # sparse plans run peer-direct by default (remote rows read by the gather over NVLink: single pass, the
-        # single-GPU bits); the pack + all-to-all-v path stays reachable and must agree
-        od_nd = torch.empty_like(od)
-        part.forward(layer, xd, od_nd, peer_direct=False)
-        st_nd = d_.last_stats()
+        # peer-direct plane (sparse plans): remote rows read by the gather over NVLink, single pass = the single-GPU bits
+        od_pd = torch.empty_like(od)
+        part.forward(layer, xd, od_pd, peer_direct=True)
+        st_pd = d_.last_stats()
         ctx.sync()
-        if st["peer_direct"]:
-            msg_ok = msg_ok and bool(torch.equal(od, od_exact)) and not st_nd["peer_direct"]
-        msg_ok = msg_ok and row_rel(od_nd.cpu().numpy(), od_exact.cpu().numpy()) <= 2e-5
+        if st_pd["peer_direct"]:
+            msg_ok = msg_ok and bool(torch.equal(od_pd, od_exact))
+        else:
+            msg_ok = msg_ok and bool(torch.equal(od_pd, od))
         out_host, out_host_exact = np.empty((hi - lo, d), np.float32), np.empty((hi - lo, d), np.float32)
         part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host)
         part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host_exact, exact=True)
@@ -101,7 +101,7 @@ def main():
             rel_o, rel_s = row_rel(full, ref), row_rel(full, single)
             plans, hosts = all(t[2] for t in gathered), all(t[3] for t in gathered)
             print(f"n={n} d={d} heads={heads} mode={mode} locality={loc}: world={world} dense={part.dense} "
-                  f"halo_rows={part.n_halo} interior_rows={part.interior_rows} passes={st['passes']} single_pass={st['exact']} peer_direct={st['peer_direct']} "
+                  f"halo_rows={part.n_halo} interior_rows={part.interior_rows} passes={st['passes']} single_pass={st['exact']} peer_direct_ran={st_pd['peer_direct']} "
                   f"overlapped: vs oracle {rel_o:.2e}, vs single GPU {rel_s:.2e}; exact bit-identical={bit}; "
                   f"plan==model {plans}; host + message-halo variants same {hosts}", flush=True)
             ok = ok and rel_o <= 1e-4 and rel_s <= 2e-5 and bit and plans and hosts
