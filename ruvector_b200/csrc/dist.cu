@@ -1123,7 +1123,8 @@ int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *P, const ruv
   };
   // K-agg (final pass) + K-upd block by block, handing finished blocks to the copy-out stream
   auto finish_range = [&](uint64_t rb, uint64_t re, const GatherPass &pass) -> int32_t {
-    const uint64_t B = dev_ptrs ? upd_block() : std::min<uint64_t>(upd_block(), 131072);
+    if (dev_ptrs) return do_aggregate_update(c, L, G, d->halo, rb, re, out_dev, true, pass);  // row-block pipeline inside
+    const uint64_t B = std::min<uint64_t>(upd_block(), 131072);
     for (uint64_t b0 = rb; b0 < re; b0 += B) {
       const uint64_t b1 = std::min(b0 + B, re);
       int32_t r = gather_rows(c, L, G, d->halo, b0, b1, pass, true);

@@ -58,6 +58,13 @@ struct ruvgnn_ctx {
   // peer-direct plane (dist.cu): the gather reads remote rows from the peers' tables; col_idx = global ids
   const ruvgnn::PeerTable *peer_dev = nullptr;
   const uint32_t *peer_cols = nullptr;
+  // Row-block pipeline of phase B (ffi.cu do_aggregate_update): K-upd of block b runs on s_upd, on
+  // upd_sms SMs, while K-agg of block b+1 runs on `stream` on the others.  blk_off = index of
+  // the current block's first row inside the per-block buffers (they are used as two halves).
+  cudaStream_t s_upd = nullptr;
+  cudaEvent_t ev_gat[2] = {}, ev_upd[2] = {};
+  uint64_t blk_off = 0;
+  bool gather_resident = false;
 };
 
 struct ruvgnn_layer {
