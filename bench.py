@@ -167,7 +167,7 @@ def kagg_roofline(H, heads, R, E, n, agg_ms, peak, peak_src, stage):
             "stage_ms": {"project": float(stage[0]), "aggregate": float(stage[1]), "update": float(stage[2])}}
 
 
-def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src):
+def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src, pipe=None, sm_total=148):
     """The six projection GEMMs against min(tensor roof, HBM roof x intensity).  USEFUL FLOPs per node
     = 2 (D H + 11 H^2) (the reference's 12 Linears); the FP32-parity path issues `passes` TF32 MMAs per product and,
     in the single-row formulation, folded matrices (issued_flops_per_node)."""
@@ -189,7 +189,10 @@ def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_
             "intensity_flop_per_byte": intensity, "algorithmic_bytes_per_node": bytes_node,
             "achieved_GBs": bytes_node * n / (gemm_ms * 1e-3) / 1e9, "frac_of_hbm": bytes_node * n / (gemm_ms * 1e-3) / 1e9 / hbm_peak,
             "useful_flops_per_node": useful_node, "issued_flops_per_node": issued_node,
-            "mma_passes_per_product": passes, "peak_source": tf32_src, "ms": gemm_ms}
+            "mma_passes_per_product": passes, "peak_source": tf32_src, "ms": gemm_ms,
+            "pipeline": (None if not pipe or not pipe.get("blocks") else
+                         {**pipe, "note": f"K-upd runs on {pipe['upd_sms']} of {sm_total} SMs beside the next block's K-agg: `ms` = K-proj + the "
+                                          f"K-upd blocks' own durations on those SMs; frac is against the whole GPU's peak"})}
 
 
 def traffic_from_profile(n, H, heads):
@@ -400,7 +403,7 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
            "projection_mode": {0: "fp32_simt", 1: "fp32_3xtf32_tcgen05", 2: "tf32_tcgen05"}[mode],
            "roofline": roof,
            "roofline_projections": gemm_roofline(d, d, heads, R, 3.0 * n, float(stage[0] + stage[2]), passes, hbm_peak,
-                                                 tf32_peak, tf32_src),
+                                                 tf32_peak, tf32_src, pipe=ctx.last_pipeline()),
            "hbm_used_gb": h.mem_used_gb(), "output_finite_sampled": finite}
     for o in layers:
         o.close()
@@ -454,6 +457,7 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
         t = ctx.last_timing()
         ctx.set_timing(False)
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
+        pipe = ctx.last_pipeline()
         # the same partition in exact mode (single-pass gather after the halo landed; bit-identical to 1 GPU)
         ms_exact = None
         if not a.exact:
@@ -477,7 +481,7 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
                "warmup": warmup, "edges_per_sec": E_total / (ms * 1e-3), "plan_build_s_rank0": round(plan_s, 3),
                "roofline": kagg_roofline(d, heads, R, float(E), float(n), float(stage[1]), hbm_peak, peak_src, stage),
                "roofline_projections": gemm_roofline(d, d, heads, R, float(n), float(stage[0] + stage[2]), passes,
-                                                     hbm_peak, tf32_peak, tf32_src),
+                                                     hbm_peak, tf32_peak, tf32_src, pipe=pipe),
                "halo": halo_block(part, dist_, stats, "overlapped multi-pass"), "check": check,
                "exact_mode": None if ms_exact is None else {
                    "ms_per_step": ms_exact, "value": n * world / (ms_exact * 1e-3),
@@ -561,6 +565,7 @@ def main():
                 layer.forward_graph_device(x_dev.data_ptr(), out_dev.data_ptr(), dg, timing=True)
             t = ctx.last_timing()
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
+        pipe_main = ctx.last_pipeline()
         E_total = h.sum_over_ranks(float(E))
         value = n * n_gpus / (ms_per_step * 1e-3)
 
@@ -599,7 +604,7 @@ def main():
                 "edges_per_sec": E_total / (ms_per_step * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                 "roofline_projections": gemm_roofline(a.dim, H, a.heads, R, float(n), float(stage[0] + stage[2]), passes,
-                                                      hbm_peak, tf32_peak, tf32_src),
+                                                      hbm_peak, tf32_peak, tf32_src, pipe=pipe_main),
             }
             if world > 1:
                 line["halo"] = halo_block(part, dist_, stats, "overlapped multi-pass")

@@ -35,6 +35,10 @@ struct ruvgnn_ctx {
   // per row block / row range / pass); created on first use
   std::vector<cudaEvent_t> agg_ev[kRing];
   uint32_t agg_used[kRing] = {};
+  // same for the K-upd blocks of the row-block pipeline (they run on s_upd beside the next gather)
+  std::vector<cudaEvent_t> upd_ev[kRing];
+  uint32_t upd_used[kRing] = {};
+  uint32_t last_pipeline_blocks = 0, last_pipeline_sms = 0;  // of the last phase B (0: sequential)
   int cur_slot = 0;
   bool timing_on = false;  // ruvgnn_ctx_set_timing: also time project / aggregate_update
   // host-buffer forward: copy streams + per-block events for the H2D | compute | D2H pipeline

@@ -113,6 +113,7 @@ void begin_timing_slot(ruvgnn_ctx *c) {
   c->cur_slot = (int)(c->ring_count % ruvgnn_ctx::kRing);
   c->ev = c->ring[c->cur_slot];
   c->agg_used[c->cur_slot] = 0;
+  c->upd_used[c->cur_slot] = 0;
   ++c->ring_count;
 }
 
@@ -555,6 +556,8 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
   const bool pipelined = upd_sms > 0 && upd_sms < c->sm_count - 16 && pass.whole() && !c->state_per_node &&
                          c->s_upd && rows >= 131072 && pb >= 16384 && rows > pb &&
                          L->mode != RUVGNN_MODE_FP32_SIMT && L->fast;
+  c->last_pipeline_blocks = pipelined ? (uint32_t)((rows + pb - 1) / pb) : 0;
+  c->last_pipeline_sms = pipelined ? (uint32_t)upd_sms : 0;
   if (!pipelined) {
     for (uint64_t b0 = rb; b0 < re; b0 += B) {
       const uint64_t b1 = b0 + B < re ? b0 + B : re;
@@ -581,12 +584,26 @@ int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_g
     if (rc) break;
     RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_gat[h], s_main));
     RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->s_upd, c->ev_gat[h], 0));
+    cudaEvent_t upd_end = nullptr;
+    if (c->timing_valid && stage_events) {
+      std::vector<cudaEvent_t> &pool = c->upd_ev[c->cur_slot];
+      uint32_t &used = c->upd_used[c->cur_slot];
+      while (pool.size() < 2 * (size_t)(used + 1)) {
+        cudaEvent_t e;
+        RUVGNN_CUDA_TRY(cudaEventCreate(&e));
+        pool.push_back(e);
+      }
+      cudaEventRecord(pool[2 * used], c->s_upd);
+      upd_end = pool[2 * used + 1];
+      ++used;
+    }
     c->stream = c->s_upd;
     c->sm_count = upd_sms;
     rc = update_rows(c, L, G, b0, b1, out_dev);
     c->stream = s_main;
     c->sm_count = sm_all;
     if (rc) break;
+    if (upd_end) cudaEventRecord(upd_end, c->s_upd);
     RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_upd[h], c->s_upd));
     used[h] = true;
   }
@@ -854,6 +871,8 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
       if (ev) cudaEventDestroy(ev);
   for (auto &pool : c->agg_ev)
     for (auto &ev : pool) cudaEventDestroy(ev);
+  for (auto &pool : c->upd_ev)
+    for (auto &ev : pool) cudaEventDestroy(ev);
   for (auto &ev : c->ev_in)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->ev_out)
@@ -880,6 +899,15 @@ int32_t ruvgnn_sync(ruvgnn_ctx *c) {
 }
 void *ruvgnn_ctx_stream(ruvgnn_ctx *c) { return c ? c->stream : nullptr; }
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
+
+int32_t ruvgnn_ctx_last_pipeline(ruvgnn_ctx *c, uint32_t *blocks, uint32_t *upd_sms) {
+  RUVGNN_ABI_TRY
+  if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
+  if (blocks) *blocks = c->last_pipeline_blocks;
+  if (upd_sms) *upd_sms = c->last_pipeline_sms;
+  return RUVGNN_OK;
+  RUVGNN_ABI_CATCH
+}
 
 int32_t ruvgnn_ctx_set_sm_limit(ruvgnn_ctx *c, int32_t sms) {
   RUVGNN_ABI_TRY
@@ -922,6 +950,14 @@ int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms6) {
     }
     if (c->agg_used[sl] == 0) RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[6], e[3]));
     upd = phase_b - agg;
+    if (c->upd_used[sl]) {  // row-block pipeline: K-upd ran beside the gathers; report its own busy time
+      upd = 0.f;
+      for (uint32_t k = 0; k < c->upd_used[sl]; ++k) {
+        float t;
+        RUVGNN_CUDA_TRY(cudaEventElapsedTime(&t, c->upd_ev[sl][2 * k], c->upd_ev[sl][2 * k + 1]));
+        upd += t;
+      }
+    }
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, e[4], e[5]));
     acc[0] += proj; acc[1] += agg; acc[2] += upd; acc[3] += h2d; acc[4] += d2h; acc[5] += xchg;
   }
