@@ -389,25 +389,31 @@ int32_t ruvgnn_partition_download(const ruvgnn_partition *p, uint32_t *col_idx_l
 
 /* Collective.  One layer over the partition: x [n_local][input_dim] -> out [n_local][hidden_dim]
  * (host pointers by default: H2D / D2H pipelined in row blocks; RUVGNN_FWD_DEVICE_PTRS: device).
- *   default     project -> exchange on the communication stream || gather pass over the own-row
- *               edges -> one gather pass per halo chunk as it lands (online-softmax state carried
- *               in HBM) -> update.  Equals the single-GPU result up to f32 summation order.
- *   RUVGNN_DIST_EXACT   single-pass gather after the whole halo has arrived, all-local row runs
- *               first: every row goes through exactly the arithmetic of the single-GPU run
- *               (bit-identical outputs).
+ *   default     project -> exchange on the communication stream (dense plane: chunked all-gather, K | V of
+ *               each chunk rebuilt while the next one is on the wire) -> single-pass gather in stored order
+ *               -> update: every row goes through exactly the arithmetic of the single-GPU run, the outputs
+ *               are bit-identical to it.  All-local row runs go first, under the exchange.
+ *               (RUVGNN_DIST_EXACT names this mode explicitly.)
+ *   RUVGNN_DIST_OVERLAP   a gather pass over the own-row edges runs while the halo is on the wire, then
+ *               one pass per halo chunk as it lands, the online-softmax state carried in HBM.  Equals the
+ *               single-GPU result up to f32 summation order.  Opt-in: on B200 a copy that runs beside the
+ *               HBM-saturating gather slows down 2.5-3x, so the passes cost more than they hide
+ *               (DESIGN.md section 6).
+ *   RUVGNN_DIST_ROW_HALO   dense plane, K|V|M layers: ship the K|V|M rows themselves.  Default there is the
+ *               message-row halo: peers ship M = W_msg x + b only (a third of the bytes) and K, V are
+ *               rebuilt on arrival with the projection's own GEMM (layer.rs:136-137), so a rebuilt row
+ *               carries the owner's bits.  (RUVGNN_DIST_MSG_HALO names the default explicitly.)
  *   RUVGNN_DIST_PEER_DIRECT   sparse plans, one process per GPU: the ranks map each other's
  *               projected tables with CUDA IPC (probed collectively at ruvgnn_dist_create) and the gather
  *               kernel reads the remote rows itself over NVLink -- no pack, no halo buffer, no collective
- *               on the data path; single pass in stored order, so the outputs are bit-identical to the
- *               single-GPU run.  Two 128-byte all-gathers per layer are the only synchronisation (tables
- *               ready / tables free).  Opt-in: the reads are not de-duplicated, so it pays only when few
- *               remote rows are referenced more than once per rank.  Ignored where IPC mapping failed.
- *   RUVGNN_DIST_MSG_HALO   dense plane, K|V|M layers: peers ship the message rows only (a third of
- *               the bytes) and K, V are rebuilt on arrival with the projection's own GEMM
- *               (layer.rs:136-137), so a rebuilt row carries the owner's bits; ignored elsewhere. */
+ *               on the data path; single pass in stored order (bit-identical to the single-GPU run).
+ *               Opt-in: the reads are not de-duplicated and SM-issued peer loads reach 290-700 GB/s, so the
+ *               pack + all-to-all-v path is faster on every graph measured.  Ignored where IPC mapping failed. */
 #define RUVGNN_DIST_EXACT 16u
 #define RUVGNN_DIST_MSG_HALO 32u
 #define RUVGNN_DIST_PEER_DIRECT 64u
+#define RUVGNN_DIST_OVERLAP 128u
+#define RUVGNN_DIST_ROW_HALO 256u
 int32_t ruvgnn_dist_forward(ruvgnn_dist *d, const ruvgnn_partition *p, const ruvgnn_layer *layer,
                             const float *x, float *out, uint32_t flags);
 typedef struct {

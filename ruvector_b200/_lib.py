@@ -117,7 +117,7 @@ class DistStats(C.Structure):
                 ("reserved", C.c_uint32)]
 
 FWD_DEVICE_PTRS, FWD_ASYNC, FWD_TIMING = 1, 2, 4
-DIST_EXACT, DIST_MSG_HALO, DIST_PEER_DIRECT = 16, 32, 64
+DIST_EXACT, DIST_MSG_HALO, DIST_PEER_DIRECT, DIST_OVERLAP, DIST_ROW_HALO = 16, 32, 64, 128, 256
 PART_DEVICE_PTRS, PART_FORCE_SPARSE, PART_FORCE_DENSE = 1, 2, 4
 NCCL_ID_BYTES = 128
 GRAPH_PRENORMALIZED, GRAPH_DEVICE_PTRS, GRAPH_NO_ACTIVE_LIST = 1, 2, 4

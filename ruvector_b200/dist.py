@@ -282,10 +282,9 @@ class Partition:
     ``device_ptrs=True`` -- objects with ``data_ptr()`` (device tensors: ``row_ptr`` int64/uint64
     ``[n_local+1]``, ``col_idx`` int32/uint32, ``edge_w`` float32).
 
-    ``forward`` / ``forward_host`` run one layer.  Default: the halo exchange overlaps a gather
-    pass over the own-row edges, then one pass per halo chunk as it lands (result equal to the
-    single-GPU run up to f32 summation order); ``exact=True``: single-pass gather after the halo
-    has arrived (bit-identical to the single-GPU run)."""
+    ``forward`` / ``forward_host`` run one layer.  Default: single-pass gather once the halo has
+    arrived, chunk by chunk (bit-identical to the single-GPU run); ``overlap=True``: a gather pass over
+    the own-row edges under the exchange, then one pass per halo chunk (equal up to f32 summation order)."""
 
     def __init__(self, dist_: Dist, bounds, row_ptr, col_idx, edge_w, device_ptrs: bool = False,
                  plane: Optional[str] = None):
@@ -344,23 +343,34 @@ class Partition:
             rc.ctypes.data_as(u64), sc.ctypes.data_as(u64)))
         return {"col_idx": col, "need_ids": need, "send_idx": send, "recv_counts": rc, "send_counts": sc}
 
-    def forward(self, layer, x_dev, out_dev, exact: bool = False, asynchronous: bool = True, msg_halo: bool = False,
-                peer_direct: bool = False):
+    @staticmethod
+    def _flags(overlap, msg_halo, peer_direct):
+        from . import _lib
+
+        f = _lib.DIST_OVERLAP if overlap else _lib.DIST_EXACT
+        if msg_halo is not None:
+            f |= _lib.DIST_MSG_HALO if msg_halo else _lib.DIST_ROW_HALO
+        return f | (_lib.DIST_PEER_DIRECT if peer_direct else 0)
+
+    def forward(self, layer, x_dev, out_dev, exact: bool = True, asynchronous: bool = True,
+                msg_halo: Optional[bool] = None, peer_direct: bool = False, overlap: bool = False):
         """Device buffers (objects with ``data_ptr()`` or raw pointers); enqueue only by default.
-        The work runs on the ctx stream (``ruvgnn_ctx_stream``): order the buffers against it."""
+        The work runs on the ctx stream (``ruvgnn_ctx_stream``): order the buffers against it.
+        ``overlap=True`` (or ``exact=False``): the multi-pass overlapped mode; ``msg_halo``: None = the
+        library's choice (message rows for K|V|M layers on the dense plane), True / False force it."""
         import ctypes as C
 
         from . import _lib
 
         xp = x_dev.data_ptr() if hasattr(x_dev, "data_ptr") else int(x_dev)
         op = out_dev.data_ptr() if hasattr(out_dev, "data_ptr") else int(out_dev)
-        flags = (_lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0) | (_lib.DIST_EXACT if exact else 0)
-                 | (_lib.DIST_MSG_HALO if msg_halo else 0) | (_lib.DIST_PEER_DIRECT if peer_direct else 0))
+        flags = (_lib.FWD_DEVICE_PTRS | (_lib.FWD_ASYNC if asynchronous else 0)
+                 | self._flags(overlap or not exact, msg_halo, peer_direct))
         _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
                                                  C.c_void_p(xp), C.c_void_p(op), flags))
 
-    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray, exact: bool = False, msg_halo: bool = False,
-                     peer_direct: bool = False):
+    def forward_host(self, layer, x_np: np.ndarray, out_np: np.ndarray, exact: bool = True,
+                     msg_halo: Optional[bool] = None, peer_direct: bool = False, overlap: bool = False):
         """Host buffers in, host buffers out (H2D / D2H inside the call, pipelined in row blocks when the
         buffers are pinned): the e2e leg of bench.py.  Blocks until the output is there."""
         import ctypes as C
@@ -373,8 +383,7 @@ class Partition:
             raise ValueError("x must be [n_local, input_dim] and out [n_local, hidden_dim]")
         _lib.check(self._lib.ruvgnn_dist_forward(self.dist.handle, self.handle, layer._device_layer(),
                                                  C.c_void_p(x_np.ctypes.data), C.c_void_p(out_np.ctypes.data),
-                                                 (_lib.DIST_EXACT if exact else 0) | (_lib.DIST_MSG_HALO if msg_halo else 0)
-                                                 | (_lib.DIST_PEER_DIRECT if peer_direct else 0)))
+                                                 self._flags(overlap or not exact, msg_halo, peer_direct)))
 
     def close(self):
         if getattr(self, "handle", None):

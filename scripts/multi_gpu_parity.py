@@ -65,14 +65,14 @@ def main():
             plan_ok = plan_ok and np.array_equal(got["col_idx"], model.graph.col_idx) and np.array_equal(got["need_ids"], model.need_ids.astype(np.uint32))
         xd = torch.from_numpy(x[lo:hi]).cuda()
         od, od_exact = torch.empty(hi - lo, d, device="cuda"), torch.empty(hi - lo, d, device="cuda")
-        part.forward(layer, xd, od)
+        part.forward(layer, xd, od, overlap=True)
         st = d_.last_stats()
-        part.forward(layer, xd, od_exact, exact=True)
+        part.forward(layer, xd, od_exact)  # default: exact
         ctx.sync()
-        # message-row halo (K, V rebuilt on arrival): the owner's bits, so exact mode stays bit-identical
+        # message-row halo (default; K, V rebuilt on arrival) vs K|V|M rows on the wire: the owner's bits either way
         od_m, od_m_exact = torch.empty_like(od), torch.empty_like(od)
-        part.forward(layer, xd, od_m, msg_halo=True)
-        part.forward(layer, xd, od_m_exact, exact=True, msg_halo=True)
+        part.forward(layer, xd, od_m, overlap=True, msg_halo=False)
+        part.forward(layer, xd, od_m_exact, msg_halo=False)  # K|V|M rows on the wire instead of message rows
         ctx.sync()
         msg_ok = bool(torch.equal(od_m_exact, od_exact)) and row_rel(od_m.cpu().numpy(), od_exact.cpu().numpy()) <= 2e-5
         # peer-direct plane (sparse plans): remote rows read by the gather over NVLink, single pass = the single-GPU bits
@@ -83,10 +83,10 @@ def main():
         if st_pd["peer_direct"]:
             msg_ok = msg_ok and bool(torch.equal(od_pd, od_exact))
         else:
-            msg_ok = msg_ok and bool(torch.equal(od_pd, od))
+            msg_ok = msg_ok and bool(torch.equal(od_pd, od_exact))
         out_host, out_host_exact = np.empty((hi - lo, d), np.float32), np.empty((hi - lo, d), np.float32)
-        part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host)
-        part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host_exact, exact=True)
+        part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host, overlap=True)
+        part.forward_host(layer, np.ascontiguousarray(x[lo:hi]), out_host_exact)
         same_host = np.array_equal(out_host, od.cpu().numpy()) and np.array_equal(out_host_exact, od_exact.cpu().numpy())
         gathered = [None] * world
         dist.all_gather_object(gathered, (od.cpu().numpy(), od_exact.cpu().numpy(), plan_ok, same_host and msg_ok))

@@ -44,9 +44,9 @@ def main():
     rp, col, w = synth_cuda.hnsw_like_graph(n, m, seed=0xBEEF + rank, locality=a.locality, n_total=n * world, row_offset=rank * n)
     part = rvdist.Partition(d_, rvdist.even_bounds(n * world, world), rp, col, w, device_ptrs=True)
     out, out_exact = torch.empty(n, d, device="cuda"), torch.empty(n, d, device="cuda")
-    part.forward(layer, x, out, asynchronous=False)
+    part.forward(layer, x, out, overlap=True, asynchronous=False)
     st = d_.last_stats()
-    part.forward(layer, x, out_exact, exact=True, asynchronous=False)
+    part.forward(layer, x, out_exact, asynchronous=False)  # default: exact
     ok = True
     if rank == 0:
         from tests.oracle_binding import Oracle

@@ -6,8 +6,8 @@
  *
  * A ring-with-chords graph over N nodes is split into equal ranges; every rank runs
  *   - the single-GPU forward of the WHOLE graph (reference bits),
- *   - ruvgnn_dist_forward in exact mode      -> must equal those bits on its own rows,
- *   - ruvgnn_dist_forward overlapped (default) -> within 2e-5 row-relative of them,
+ *   - ruvgnn_dist_forward (default = exact mode) -> must equal those bits on its own rows,
+ *   - ruvgnn_dist_forward RUVGNN_DIST_OVERLAP    -> within 2e-5 row-relative of them,
  * through both data planes. */
 #define _POSIX_C_SOURCE 200809L
 #include <math.h>
@@ -94,9 +94,12 @@ static void *rank_main(void *arg) {
     memset(out, 0, n * H * sizeof *out);
     CHECK(rank, ruvgnn_dist_forward(dist, part, layer, g_x + lo * D, out, RUVGNN_DIST_EXACT) == RUVGNN_OK);
     CHECK(rank, memcmp(out, g_ref + lo * H, n * H * sizeof *out) == 0);
+    memset(out, 0, n * H * sizeof *out);
+    CHECK(rank, ruvgnn_dist_forward(dist, part, layer, g_x + lo * D, out, 0) == RUVGNN_OK); /* the default IS the exact mode */
+    CHECK(rank, memcmp(out, g_ref + lo * H, n * H * sizeof *out) == 0);
     /* overlapped multi-pass mode: same values up to f32 summation order */
     memset(out, 0, n * H * sizeof *out);
-    CHECK(rank, ruvgnn_dist_forward(dist, part, layer, g_x + lo * D, out, 0) == RUVGNN_OK);
+    CHECK(rank, ruvgnn_dist_forward(dist, part, layer, g_x + lo * D, out, RUVGNN_DIST_OVERLAP) == RUVGNN_OK);
     const double rel = max_row_rel(out, g_ref + lo * H, (int)n);
     CHECK(rank, rel <= 2e-5);
     ruvgnn_dist_stats st;
