@@ -416,7 +416,8 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
     return blk
 
 
-def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, heads, config, lams=(0.0, 0.9)):
+def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, heads, config, lams=(0.0, 0.9),
+                          msg_halo=None, time_overlap=True):
     """A range-partitioned configuration generated on the device: n nodes x d x heads per GPU, M=32, one layer, halo
     exchange inside the library; one block per locality value."""
     import ruvector_b200 as rv
@@ -450,24 +451,24 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
         del rp, col, w
         torch.cuda.empty_cache()
         steps, warmup = max(2, min(a.steps, 5)), 3
-        ms = h.timed(lambda: part.forward(layer, x, out, overlap=a.overlap, peer_direct=a.peer_direct), steps, warmup)
+        ms = h.timed(lambda: part.forward(layer, x, out, overlap=a.overlap, peer_direct=a.peer_direct, msg_halo=msg_halo), steps, warmup)
         stats = dist_.last_stats()
         ctx.set_timing(True)
         for _ in range(2):
-            part.forward(layer, x, out, overlap=a.overlap, peer_direct=a.peer_direct)
+            part.forward(layer, x, out, overlap=a.overlap, peer_direct=a.peer_direct, msg_halo=msg_halo)
         t = ctx.last_timing()
         ctx.set_timing(False)
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
         pipe = ctx.last_pipeline()
         # the same partition in the overlapped multi-pass mode, timed, and checked against the default (exact) result
         ms_other, check = None, None
-        if not a.overlap:
-            ms_other = h.timed(lambda: part.forward(layer, x, out, overlap=True), 3, 1)
+        if not a.overlap and time_overlap:
+            ms_other = h.timed(lambda: part.forward(layer, x, out, overlap=True, msg_halo=msg_halo), 3, 1)
             stats_other = dist_.last_stats()
             if out2 is None:
                 out2 = torch.empty_like(out)
-            part.forward(layer, x, out2, overlap=True, asynchronous=False)
-            part.forward(layer, x, out, asynchronous=False)
+            part.forward(layer, x, out2, overlap=True, asynchronous=False, msg_halo=msg_halo)
+            part.forward(layer, x, out, asynchronous=False, msg_halo=msg_halo)
             sl = slice(0, n, max(n // 65536, 1))
             num = (out2[sl] - out[sl]).norm(dim=1)
             den = out[sl].norm(dim=1).clamp_min(1e-6)
@@ -625,6 +626,17 @@ def main():
         torch.cuda.empty_cache()
 
     if not a.no_secondary:
+        # Safety net: the secondary configurations are large (up to ~150 GB of HBM per GPU).  If they hang
+        # (a rank lost to an out-of-memory error inside a collective) the config-2 line must still come out.
+        def _bail():
+            if rank == 0 and line is not None:
+                line["secondary"] = {"error": "secondary configurations timed out after 420 s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        watchdog = threading.Timer(420.0, _bail)
+        watchdog.daemon = True
+        watchdog.start()
         try:
             if world == 1:
                 sec = secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src)
@@ -639,12 +651,15 @@ def main():
                 if a.secondary_nodes == 0 and world >= 8:
                     sec["config4"] = secondary_partitioned(
                         h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n4, 768, 8,
-                        f"10M nodes d=768, 8 heads, M=32, sharded with halo exchange (BASELINE configs[3]): {n4} nodes per GPU")
+                        f"10M nodes d=768, 8 heads, M=32, sharded with halo exchange (BASELINE configs[3]): {n4} nodes per GPU; "
+                        f"K|V|M rows on the wire (the message-row halo's staging buffer does not fit beside the 92 GB halo)",
+                        msg_halo=False, time_overlap=False)
                 elif a.secondary_nodes == 0:
                     sec["config4"] = {"skipped": f"10M x 768 at locality 0 needs the K|V|M rows of all 10M nodes per GPU "
                                                  f"(92 GB) + {n4} own rows x 12 KB: run at 8 GPUs"}
-        except rv.GnnError as e:  # reported, never silently dropped
-            sec = {"error": f"{type(e).__name__}: {e}"}
+        except (rv.GnnError, RuntimeError, MemoryError) as e:  # reported, never silently dropped
+            sec = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        watchdog.cancel()
         if rank == 0:
             if line is None:
                 line = {"metric": METRIC, "n_gpus": n_gpus, "secondary_only": True}
