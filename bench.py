@@ -168,7 +168,7 @@ def kagg_roofline(H, heads, R, E, n, agg_ms, peak, peak_src, stage):
             "stage_ms": {"project": float(stage[0]), "aggregate": float(stage[1]), "update": float(stage[2])}}
 
 
-def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src, pipe=None, sm_total=148):
+def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src):
     """The six projection GEMMs against min(tensor roof, HBM roof x intensity).  USEFUL FLOPs per node
     = 2 (D H + 11 H^2) (the reference's 12 Linears); the FP32-parity path issues `passes` TF32 MMAs per product and,
     in the single-row formulation, folded matrices (issued_flops_per_node)."""
@@ -190,10 +190,7 @@ def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_
             "intensity_flop_per_byte": intensity, "algorithmic_bytes_per_node": bytes_node,
             "achieved_GBs": bytes_node * n / (gemm_ms * 1e-3) / 1e9, "frac_of_hbm": bytes_node * n / (gemm_ms * 1e-3) / 1e9 / hbm_peak,
             "useful_flops_per_node": useful_node, "issued_flops_per_node": issued_node,
-            "mma_passes_per_product": passes, "peak_source": tf32_src, "ms": gemm_ms,
-            "pipeline": (None if not pipe or not pipe.get("blocks") else
-                         {**pipe, "note": f"K-upd runs on {pipe['upd_sms']} of {sm_total} SMs beside the next block's K-agg: `ms` = K-proj + the "
-                                          f"K-upd blocks' own durations on those SMs; frac is against the whole GPU's peak"})}
+            "mma_passes_per_product": passes, "peak_source": tf32_src, "ms": gemm_ms}
 
 
 def traffic_from_profile(n, H, heads):
@@ -404,7 +401,7 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
            "projection_mode": {0: "fp32_simt", 1: "fp32_3xtf32_tcgen05", 2: "tf32_tcgen05"}[mode],
            "roofline": roof,
            "roofline_projections": gemm_roofline(d, d, heads, R, 3.0 * n, float(stage[0] + stage[2]), passes, hbm_peak,
-                                                 tf32_peak, tf32_src, pipe=ctx.last_pipeline()),
+                                                 tf32_peak, tf32_src),
            "hbm_used_gb": h.mem_used_gb(), "output_finite_sampled": finite}
     for o in layers:
         o.close()
@@ -459,7 +456,6 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
         t = ctx.last_timing()
         ctx.set_timing(False)
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
-        pipe = ctx.last_pipeline()
         # the same partition in the overlapped multi-pass mode, timed, and checked against the default (exact) result
         ms_other, check = None, None
         if not a.overlap and time_overlap:
@@ -480,7 +476,7 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
                "warmup": warmup, "edges_per_sec": E_total / (ms * 1e-3), "plan_build_s_rank0": round(plan_s, 3),
                "roofline": kagg_roofline(d, heads, R, float(E), float(n), float(stage[1]), hbm_peak, peak_src, stage),
                "roofline_projections": gemm_roofline(d, d, heads, R, float(n), float(stage[0] + stage[2]), passes,
-                                                     hbm_peak, tf32_peak, tf32_src, pipe=pipe),
+                                                     hbm_peak, tf32_peak, tf32_src),
                "halo": halo_block(part, dist_, stats, "overlapped multi-pass"), "check": check,
                "overlap_mode": None if ms_other is None else {
                    "ms_per_step": ms_other, "value": n * world / (ms_other * 1e-3), "gather_passes": stats_other["passes"],
@@ -565,7 +561,6 @@ def main():
                 layer.forward_graph_device(x_dev.data_ptr(), out_dev.data_ptr(), dg, timing=True)
             t = ctx.last_timing()
         stage = np.array([t["project_ms"], t["aggregate_ms"], t["update_ms"]])
-        pipe_main = ctx.last_pipeline()
         E_total = h.sum_over_ranks(float(E))
         value = n * n_gpus / (ms_per_step * 1e-3)
 
@@ -604,7 +599,7 @@ def main():
                 "edges_per_sec": E_total / (ms_per_step * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                 "roofline_projections": gemm_roofline(a.dim, H, a.heads, R, float(n), float(stage[0] + stage[2]), passes,
-                                                      hbm_peak, tf32_peak, tf32_src, pipe=pipe_main),
+                                                      hbm_peak, tf32_peak, tf32_src),
             }
             if world > 1:
                 line["halo"] = halo_block(part, dist_, stats, "overlapped multi-pass")

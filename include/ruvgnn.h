@@ -61,12 +61,8 @@ uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *ctx);
 /* Device milliseconds per stage (0 project, 1 aggregate, 2 update, 3 h2d, 4 d2h,
  * 5 halo exchange wait), averaged over the timed forwards (up to 32) since the
  * previous query; CUDA events on the launching stream.  Synchronises the stream.
- * aggregate = sum over the K-agg launches.  When phase B ran as a row-block pipeline (K-upd of block b
- * on a second stream, on `upd_sms` SMs, beside K-agg of block b+1) update = the sum of the K-upd
- * blocks' own durations on those SMs, so the stages overlap and no longer add up to the layer time. */
+ * aggregate = sum over the K-agg launches (one per row block / row range / gather pass). */
 int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *ctx, float *ms6);
-/* Row blocks and SMs given to K-upd in the last phase B (0, 0: it ran sequentially). */
-int32_t ruvgnn_ctx_last_pipeline(ruvgnn_ctx *ctx, uint32_t *blocks, uint32_t *upd_sms);
 /* Launch grids sized for at most `sms` SMs (0 = all of the device; negative = all but
  * |sms|): leaves SMs to a collective that runs concurrently on another stream, so persistent
  * kernels do not queue behind its blocks. */

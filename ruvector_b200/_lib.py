@@ -39,7 +39,6 @@ SYMBOLS = {
     "ruvgnn_ctx_stream": (_vp, [_vp]),
     "ruvgnn_ctx_launch_count": (C.c_uint64, [_vp]),
     "ruvgnn_ctx_last_timing": (C.c_int32, [_vp, c_float_p]),
-    "ruvgnn_ctx_last_pipeline": (C.c_int32, [_vp, _u32p, _u32p]),
     "ruvgnn_ctx_set_timing": (C.c_int32, [_vp, C.c_int32]),
     "ruvgnn_ctx_set_sm_limit": (C.c_int32, [_vp, C.c_int32]),
     "ruvgnn_layer_create": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(Weights), C.POINTER(_vp)]),

@@ -118,7 +118,6 @@ struct GatherArgs {
   int npass1 = 0, pass = 0;
   float *ml = nullptr;
   const PeerTable *peer = nullptr;  // device pointer; non-null: peer-direct plane (col_idx = global ids)
-  int resident = 0;  // size the grid so that every CTA is resident at once (row-block pipeline)
 };
 cudaError_t launch_gather(const GatherArgs &a, bool fast, int sm_count, cudaStream_t s,
                           uint64_t *launches);
@@ -148,7 +147,6 @@ struct GatherR1Args {
   int npass1 = 0, pass = 0;
   float *ml = nullptr;
   const PeerTable *peer = nullptr;  // as in GatherArgs
-  int resident = 0;
 };
 cudaError_t launch_gather_r1(const GatherR1Args &a, int sm_count, cudaStream_t s, uint64_t *launches);
 // Pass-ordered copy of a CSR's edge arrays for the multi-pass gather: pass p = the columns in

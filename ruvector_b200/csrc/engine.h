@@ -35,10 +35,6 @@ struct ruvgnn_ctx {
   // per row block / row range / pass); created on first use
   std::vector<cudaEvent_t> agg_ev[kRing];
   uint32_t agg_used[kRing] = {};
-  // same for the K-upd blocks of the row-block pipeline (they run on s_upd beside the next gather)
-  std::vector<cudaEvent_t> upd_ev[kRing];
-  uint32_t upd_used[kRing] = {};
-  uint32_t last_pipeline_blocks = 0, last_pipeline_sms = 0;  // of the last phase B (0: sequential)
   int cur_slot = 0;
   bool timing_on = false;  // ruvgnn_ctx_set_timing: also time project / aggregate_update
   // host-buffer forward: copy streams + per-block events for the H2D | compute | D2H pipeline
@@ -62,13 +58,6 @@ struct ruvgnn_ctx {
   // peer-direct plane (dist.cu): the gather reads remote rows from the peers' tables; col_idx = global ids
   const ruvgnn::PeerTable *peer_dev = nullptr;
   const uint32_t *peer_cols = nullptr;
-  // Row-block pipeline of phase B (ffi.cu do_aggregate_update): K-upd of block b runs on s_upd, on
-  // upd_sms SMs, while K-agg of block b+1 runs on `stream` on the others.  blk_off = index of
-  // the current block's first row inside the per-block buffers (they are used as two halves).
-  cudaStream_t s_upd = nullptr;
-  cudaEvent_t ev_gat[2] = {}, ev_upd[2] = {};
-  uint64_t blk_off = 0;
-  bool gather_resident = false;
 };
 
 struct ruvgnn_layer {

@@ -113,7 +113,6 @@ void begin_timing_slot(ruvgnn_ctx *c) {
   c->cur_slot = (int)(c->ring_count % ruvgnn_ctx::kRing);
   c->ev = c->ring[c->cur_slot];
   c->agg_used[c->cur_slot] = 0;
-  c->upd_used[c->cur_slot] = 0;
   ++c->ring_count;
 }
 
@@ -242,7 +241,7 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
   if (!pass.whole() && !c->state_per_node)
     return fail(RUVGNN_ERR_INVALID_INPUT, "multi-pass gather needs per-node gather state");
   Ws w = carve(c, L, n);
-  const int64_t sb = c->state_per_node ? 0 : (int64_t)rb - (int64_t)c->blk_off;
+  const int64_t sb = c->state_per_node ? 0 : (int64_t)rb;
   cudaEvent_t agg_end = nullptr;
   if (c->timing_valid && stage_events) {
     std::vector<cudaEvent_t> &pool = c->agg_ev[c->cur_slot];
@@ -288,7 +287,6 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
       ga.peer = c->peer_dev;
       ga.col_idx = c->peer_cols;
     }
-    ga.resident = c->gather_resident ? 1 : 0;
     RUVGNN_CUDA_TRY(launch_gather(ga, L->fast, c->sm_count, c->stream, &c->launches));
   } else {
     GatherR1Args ga;
@@ -321,7 +319,6 @@ int32_t gather_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
       ga.peer = c->peer_dev;
       ga.col_idx = c->peer_cols;
     }
-    ga.resident = c->gather_resident ? 1 : 0;
     RUVGNN_CUDA_TRY(launch_gather_r1(ga, c->sm_count, c->stream, &c->launches));
   }
   if (agg_end) {
@@ -419,8 +416,8 @@ int32_t update_rows(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
   Ws w = carve(c, L, c->proj_rows);
   // T0..T3 hold rows [rb, re) only (row r at index r - rb); OA / SA likewise unless the gather
   // state is kept per node.
-  const int64_t sb = c->state_per_node ? 0 : (int64_t)rb - (int64_t)c->blk_off;
-  const int64_t tb = (int64_t)rb - (int64_t)c->blk_off;
+  const int64_t sb = c->state_per_node ? 0 : (int64_t)rb;
+  const int64_t tb = (int64_t)rb;
   UpdIO io;
   io.oa = L->r1 ? w.SA - (ptrdiff_t)(sb * (int64_t)(L->heads + 1) * H) : w.OA - (ptrdiff_t)(sb * 2 * H);
   io.m = w.m;
@@ -523,97 +520,21 @@ int32_t forward_device(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph 
   return do_aggregate_update(c, L, G, nullptr, 0, n, out_dev);
 }
 
-// Phase B over rows [rb, re): K-agg -> K-upd per row block.
-//
-// Pipelined form (default for single-pass gathers over >= 2 blocks): the rows are cut into blocks of
-// `pb` rows; K-upd of block b runs on the update stream, on upd_sms SMs (its persistent GEMM grids are
-// sized for that many), while K-agg of block b+1 runs on the launching stream on the remaining SMs.
-// K-agg is HBM-bound and leaves the tensor pipe idle, K-upd is tensor / latency-bound and moves ~12% of
-// the HBM rate, so the two overlap instead of adding up.  The per-block buffers are used as two halves.
-// The update stream has the higher priority, so when a gather ends the pending GEMM CTAs are placed
-// first and the next gather's CTAs fill the other SMs (a GEMM CTA takes a whole SM's shared memory and
-// registers: the two kinds never share an SM).  Same arithmetic per row as the sequential form.
-static int pipeline_sms() {
-  static int v = -2;
-  if (v == -2) {
-    const char *e = getenv("RUVGNN_UPD_SMS");  // 0 disables the pipeline
-    v = e ? atoi(e) : 48;
-    if (v < 0 || v > 120) v = 48;
-  }
-  return v;
-}
-
+// Phase B over rows [rb, re): one K-agg -> K-upd pass per block of at most upd_block() rows.
+// (Round 2 tried running K-upd of block b on a second, high-priority stream on 32-64 SMs beside K-agg of
+// block b+1: the two contend for L2 / HBM instead of overlapping -- config 2 went from 53.4 to 59.2 ms,
+// 4M x 128 from 41.6 to 50.4 ms, profiles/r02h_bench_*_pipeline*.json -- so the blocks run back to back.)
 int32_t do_aggregate_update(ruvgnn_ctx *c, const ruvgnn_layer *L, const ruvgnn_graph *G,
                             const float *halo, uint64_t rb, uint64_t re, float *out_dev,
                             bool stage_events, const GatherPass &pass) {
   const uint64_t B = upd_block();
-  const uint64_t rows = re > rb ? re - rb : 0;
-  const uint64_t cap = c->proj_rows < B ? c->proj_rows : B;  // rows the per-block buffers hold
-  const int upd_sms = pipeline_sms();
-  uint64_t pb = ((rows + 7) / 8 + 127) / 128 * 128;  // ~8 blocks
-  if (pb < 32768) pb = 32768;
-  if (pb > cap / 2) pb = cap / 2 / 128 * 128;
-  const bool pipelined = upd_sms > 0 && upd_sms < c->sm_count - 16 && pass.whole() && !c->state_per_node &&
-                         c->s_upd && rows >= 131072 && pb >= 16384 && rows > pb &&
-                         L->mode != RUVGNN_MODE_FP32_SIMT && L->fast;
-  c->last_pipeline_blocks = pipelined ? (uint32_t)((rows + pb - 1) / pb) : 0;
-  c->last_pipeline_sms = pipelined ? (uint32_t)upd_sms : 0;
-  if (!pipelined) {
-    for (uint64_t b0 = rb; b0 < re; b0 += B) {
-      const uint64_t b1 = b0 + B < re ? b0 + B : re;
-      int32_t rc = gather_rows(c, L, G, halo, b0, b1, pass, stage_events);
-      if (!rc) rc = update_rows(c, L, G, b0, b1, out_dev);
-      if (rc) return rc;
-    }
-    return RUVGNN_OK;
+  for (uint64_t b0 = rb; b0 < re; b0 += B) {
+    const uint64_t b1 = b0 + B < re ? b0 + B : re;
+    int32_t rc = gather_rows(c, L, G, halo, b0, b1, pass, stage_events);
+    if (!rc) rc = update_rows(c, L, G, b0, b1, out_dev);
+    if (rc) return rc;
   }
-  cudaStream_t s_main = c->stream;
-  const int sm_all = c->sm_count;
-  int32_t rc = RUVGNN_OK;
-  uint64_t k = 0;
-  bool used[2] = {false, false};
-  for (uint64_t b0 = rb; b0 < re && !rc; b0 += pb, ++k) {
-    const uint64_t b1 = b0 + pb < re ? b0 + pb : re;
-    const int h = (int)(k & 1);
-    if (used[h]) RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s_main, c->ev_upd[h], 0));  // this half is free again
-    c->blk_off = (uint64_t)h * pb;  // row r of the block uses index r - b0 + h * pb of the per-block buffers
-    c->sm_count = k == 0 ? sm_all : sm_all - upd_sms;
-    c->gather_resident = true;  // every gather CTA resident at once: none is left to grab the update's SMs
-    rc = gather_rows(c, L, G, halo, b0, b1, pass, stage_events);
-    c->gather_resident = false;
-    if (rc) break;
-    RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_gat[h], s_main));
-    RUVGNN_CUDA_TRY(cudaStreamWaitEvent(c->s_upd, c->ev_gat[h], 0));
-    cudaEvent_t upd_end = nullptr;
-    if (c->timing_valid && stage_events) {
-      std::vector<cudaEvent_t> &pool = c->upd_ev[c->cur_slot];
-      uint32_t &used = c->upd_used[c->cur_slot];
-      while (pool.size() < 2 * (size_t)(used + 1)) {
-        cudaEvent_t e;
-        RUVGNN_CUDA_TRY(cudaEventCreate(&e));
-        pool.push_back(e);
-      }
-      cudaEventRecord(pool[2 * used], c->s_upd);
-      upd_end = pool[2 * used + 1];
-      ++used;
-    }
-    c->stream = c->s_upd;
-    c->sm_count = upd_sms;
-    rc = update_rows(c, L, G, b0, b1, out_dev);
-    c->stream = s_main;
-    c->sm_count = sm_all;
-    if (rc) break;
-    if (upd_end) cudaEventRecord(upd_end, c->s_upd);
-    RUVGNN_CUDA_TRY(cudaEventRecord(c->ev_upd[h], c->s_upd));
-    used[h] = true;
-  }
-  c->stream = s_main;
-  c->sm_count = sm_all;
-  c->blk_off = 0;
-  c->gather_resident = false;
-  for (int h = 0; h < 2; ++h)
-    if (used[h]) RUVGNN_CUDA_TRY(cudaStreamWaitEvent(s_main, c->ev_upd[h], 0));
-  return rc;
+  return RUVGNN_OK;
 }
 
 }  // namespace ruvgnn
@@ -836,15 +757,6 @@ int32_t ruvgnn_ctx_create(int32_t device, void *stream, ruvgnn_ctx **out) {
   RUVGNN_CUDA_TRY(cudaMalloc(&c->d_flag, sizeof(int)));
   for (auto &slot : c->ring)
     for (auto &ev : slot) RUVGNN_CUDA_TRY(cudaEventCreate(&ev));
-  {
-    int lo_prio = 0, hi_prio = 0;
-    RUVGNN_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
-    RUVGNN_CUDA_TRY(cudaStreamCreateWithPriority(&c->s_upd, cudaStreamNonBlocking, hi_prio));
-    for (int i = 0; i < 2; ++i) {
-      RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_gat[i], cudaEventDisableTiming));
-      RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_upd[i], cudaEventDisableTiming));
-    }
-  }
   RUVGNN_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   RUVGNN_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   for (auto &ev : c->ev_in) RUVGNN_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -871,19 +783,12 @@ void ruvgnn_ctx_destroy(ruvgnn_ctx *c) {
       if (ev) cudaEventDestroy(ev);
   for (auto &pool : c->agg_ev)
     for (auto &ev : pool) cudaEventDestroy(ev);
-  for (auto &pool : c->upd_ev)
-    for (auto &ev : pool) cudaEventDestroy(ev);
   for (auto &ev : c->ev_in)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->ev_out)
     if (ev) cudaEventDestroy(ev);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
-  for (int i = 0; i < 2; ++i) {
-    if (c->ev_gat[i]) cudaEventDestroy(c->ev_gat[i]);
-    if (c->ev_upd[i]) cudaEventDestroy(c->ev_upd[i]);
-  }
-  if (c->s_upd) cudaStreamDestroy(c->s_upd);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -899,15 +804,6 @@ int32_t ruvgnn_sync(ruvgnn_ctx *c) {
 }
 void *ruvgnn_ctx_stream(ruvgnn_ctx *c) { return c ? c->stream : nullptr; }
 uint64_t ruvgnn_ctx_launch_count(ruvgnn_ctx *c) { return c ? c->launches : 0; }
-
-int32_t ruvgnn_ctx_last_pipeline(ruvgnn_ctx *c, uint32_t *blocks, uint32_t *upd_sms) {
-  RUVGNN_ABI_TRY
-  if (!c) return fail(RUVGNN_ERR_INVALID_INPUT, "ctx is null");
-  if (blocks) *blocks = c->last_pipeline_blocks;
-  if (upd_sms) *upd_sms = c->last_pipeline_sms;
-  return RUVGNN_OK;
-  RUVGNN_ABI_CATCH
-}
 
 int32_t ruvgnn_ctx_set_sm_limit(ruvgnn_ctx *c, int32_t sms) {
   RUVGNN_ABI_TRY
@@ -950,14 +846,6 @@ int32_t ruvgnn_ctx_last_timing(ruvgnn_ctx *c, float *ms6) {
     }
     if (c->agg_used[sl] == 0) RUVGNN_CUDA_TRY(cudaEventElapsedTime(&agg, e[6], e[3]));
     upd = phase_b - agg;
-    if (c->upd_used[sl]) {  // row-block pipeline: K-upd ran beside the gathers; report its own busy time
-      upd = 0.f;
-      for (uint32_t k = 0; k < c->upd_used[sl]; ++k) {
-        float t;
-        RUVGNN_CUDA_TRY(cudaEventElapsedTime(&t, c->upd_ev[sl][2 * k], c->upd_ev[sl][2 * k + 1]));
-        upd += t;
-      }
-    }
     RUVGNN_CUDA_TRY(cudaEventElapsedTime(&d2h, e[4], e[5]));
     acc[0] += proj; acc[1] += agg; acc[2] += upd; acc[3] += h2d; acc[4] += d2h; acc[5] += xchg;
   }

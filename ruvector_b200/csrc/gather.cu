@@ -896,8 +896,7 @@ cudaError_t launch_r1_h(const GatherR1Args &a, float scale_log2, int sm_count, c
   }
   if constexpr (HEADS <= 4) {
     if (batched) {
-      const uint64_t per_sm = a.resident ? 16 : 64;  // 16 one-warp blocks are resident per SM
-      uint64_t warps = rows < (uint64_t)sm_count * per_sm ? rows : (uint64_t)sm_count * per_sm;
+      uint64_t warps = rows < (uint64_t)sm_count * 64 ? rows : (uint64_t)sm_count * 64;
       static int pf = -1;  // RUVGNN_R1_PF=0: no L1 prefetch of the next step's rows (A/B runs)
       if (pf < 0) {
         const char *e = getenv("RUVGNN_R1_PF");
@@ -924,9 +923,8 @@ cudaError_t launch_fast_p(const GatherArgs &a, float inv_scale, int sm_count, cu
   const uint64_t rows = a.row_end - a.row_begin;
   const int wpb = 4;
   uint64_t blocks = (rows + wpb - 1) / wpb;
-  // grid-stride: a few resident waves, a multiple of the SM count (resident: exactly the 4 CTAs an SM
-  // holds at 110-128 registers, so no CTA waits in the queue)
-  const uint64_t cap = (uint64_t)sm_count * (a.resident ? 4 : 16);
+  // grid-stride: a few resident waves, a multiple of the SM count
+  const uint64_t cap = (uint64_t)sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return cudaSuccess;
   dim3 grid((unsigned)blocks), block(32 * wpb);

@@ -64,12 +64,6 @@ class Context:
         _lib.check(self._lib.ruvgnn_ctx_last_timing(self.handle, ms))
         return dict(zip(("project_ms", "aggregate_ms", "update_ms", "h2d_ms", "d2h_ms", "exchange_ms"), map(float, ms)))
 
-    def last_pipeline(self) -> dict:
-        """Row blocks / SMs given to K-upd in the last phase B (zeros: it ran sequentially)."""
-        b, s = C.c_uint32(), C.c_uint32()
-        _lib.check(self._lib.ruvgnn_ctx_last_pipeline(self.handle, C.byref(b), C.byref(s)))
-        return {"blocks": int(b.value), "upd_sms": int(s.value)}
-
     def set_timing(self, on: bool):
         _lib.check(self._lib.ruvgnn_ctx_set_timing(self.handle, 1 if on else 0))
 
