@@ -423,7 +423,7 @@ typedef struct {
 } ruvgnn_dist_stats;
 /* Synchronises the ctx stream. */
 int32_t ruvgnn_dist_last_stats(ruvgnn_dist *d, ruvgnn_dist_stats *out);
-/* Row chunks of the dense plane (1..16; 0 = default: 1 / 2 / 4 chunks for up to 2 / 4 / more ranks)
+/* Row chunks of the dense plane (1..16; 0 = default: 4)
  * for partitions created afterwards: the all-gather runs chunk by chunk and the overlapped forward
  * runs one gather pass per chunk. */
 int32_t ruvgnn_dist_set_chunks(ruvgnn_dist *d, uint32_t chunks);

@@ -794,10 +794,10 @@ int32_t ruvgnn_partition_create(ruvgnn_dist *d, const uint64_t *bounds, const ui
   P->dense = dense;
 
   if (dense) {
-    // Each chunk costs one more gather pass (state re-read, ragged edge groups), so chunks pay off
-    // only while the wire time they hide exceeds that: with 2 ranks the pass over the own-row
-    // edges alone outlasts the exchange (1 chunk); with 8 the exchange dominates (4 chunks).
-    uint32_t chunks = d->chunks ? d->chunks : (world <= 2 ? 1u : world <= 4 ? 2u : 4u);
+    // Chunks let K | V of chunk k be rebuilt while chunk k+1 is on the wire (message-row halo), and in
+    // the opt-in overlapped mode each chunk is one more gather pass.  4 measured best or equal at 2 and
+    // 8 ranks (profiles/r02i_n2_*.json, r02g_n8_*.json).
+    uint32_t chunks = d->chunks ? d->chunks : 4u;
     if ((uint64_t)chunks > n) chunks = (uint32_t)(n ? n : 1);
     P->starts.resize(chunks + 1);
     for (uint32_t k = 0; k <= chunks; ++k) P->starts[k] = (n * k) / chunks;
