@@ -168,19 +168,23 @@ def kagg_roofline(H, heads, R, E, n, agg_ms, peak, peak_src, stage):
             "stage_ms": {"project": float(stage[0]), "aggregate": float(stage[1]), "update": float(stage[2])}}
 
 
-def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src):
+def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src, msg_only_rows=0.0):
     """The six projection GEMMs against min(tensor roof, HBM roof x intensity).  USEFUL FLOPs per node
     = 2 (D H + 11 H^2) (the reference's 12 Linears); the FP32-parity path issues `passes` TF32 MMAs per product and,
-    in the single-row formulation, folded matrices (issued_flops_per_node)."""
+    in the single-row formulation, folded matrices (issued_flops_per_node).  `msg_only_rows`: rows without
+    neighbours on a sparse level, which only go through W_msg and the LayerNorm (layer.rs:385-389)."""
     if not gemm_ms or gemm_ms <= 0:
         return None
     useful_node = 2.0 * (D * H + 11.0 * H * H)
     units = (2 * heads + 7) if R == 1 else 11  # H x H units: W_qk, W_ov (h each), W_agg, gates (4), candidate (2)
     issued_node = 2.0 * (D * H + units * H * H) * passes
     bytes_node = proj_bytes_per_node(D, H, R, heads)
-    useful = useful_node * n / (gemm_ms * 1e-3) / 1e12
-    issued = issued_node * n / (gemm_ms * 1e-3) / 1e12
-    intensity = issued_node / bytes_node  # MMA FLOPs the pipe must issue per HBM byte
+    useful_total = useful_node * n + 2.0 * D * H * msg_only_rows
+    issued_total = issued_node * n + 2.0 * D * H * passes * msg_only_rows
+    bytes_total = bytes_node * n + (4.0 * D + 12.0 * H) * msg_only_rows
+    useful = useful_total / (gemm_ms * 1e-3) / 1e12
+    issued = issued_total / (gemm_ms * 1e-3) / 1e12
+    intensity = issued_total / bytes_total  # MMA FLOPs the pipe must issue per HBM byte
     hbm_bound_tflops = hbm_peak * 1e9 * intensity / 1e12
     bound = min(tf32_peak, hbm_bound_tflops)
     return {"kernels": "gemm_tc_kernel / gemm_tc_ts_kernel (K-proj + K-upd, 6 GEMMs + LayerNorm)",
@@ -188,8 +192,9 @@ def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_
             "achieved": issued, "achieved_useful": useful, "peak": bound, "frac": issued / bound,
             "frac_useful": useful / bound, "tensor_peak": tf32_peak, "hbm_bound_tflops": hbm_bound_tflops,
             "intensity_flop_per_byte": intensity, "algorithmic_bytes_per_node": bytes_node,
-            "achieved_GBs": bytes_node * n / (gemm_ms * 1e-3) / 1e9, "frac_of_hbm": bytes_node * n / (gemm_ms * 1e-3) / 1e9 / hbm_peak,
+            "achieved_GBs": bytes_total / (gemm_ms * 1e-3) / 1e9, "frac_of_hbm": bytes_total / (gemm_ms * 1e-3) / 1e9 / hbm_peak,
             "useful_flops_per_node": useful_node, "issued_flops_per_node": issued_node,
+            "rows_full_chain": n, "rows_message_only": msg_only_rows,
             "mma_passes_per_product": passes, "peak_source": tf32_src, "ms": gemm_ms}
 
 
@@ -370,11 +375,12 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
     ctx = rv.Context(h.local, h.stream.cuda_stream)
     x = synth_cuda.make_features(n, d, seed=0x5EED)
     levels = [2, 1, 0]
-    graphs, edges = [], []
+    graphs, edges, active = [], [], []
     for lv in levels:
         rp, col, w = synth_cuda.hnsw_like_graph(n, m, seed=0xBEEF, level=lv)
         graphs.append(rv.DeviceGraph(ctx, rp, col, w))
         edges.append(int(col.numel()))
+        active.append(int(((rp[1:] - rp[:-1]) > 0).sum().item()))
         del rp, col, w
     torch.cuda.empty_cache()
     layers = [rv.RuvectorLayer(d, d, heads, 0.1, weights=synth.make_weights(d, d, seed=0xC0FFEE + 17 * l), ctx=ctx)
@@ -390,8 +396,11 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
     passes = 3 if mode == _lib.MODE_FP32_TC else 1
     R = int(_lib.load().ruvgnn_layer_halo_width(layers[0]._device_layer())) // d
     E = float(sum(edges))
-    roof = kagg_roofline(d, heads, R, E, 3.0 * n, float(stage[1]), hbm_peak, peak_src, stage)
-    roof["note"] = "three K-agg launches per step (levels 2, 1, 0); bytes and time summed"
+    # sparse levels (fewer than half of the rows active) run gather and update on the active rows only
+    full = float(sum(a_ if 2 * a_ < n else n for a_ in active))
+    msg_only = float(3 * n) - full
+    roof = kagg_roofline(d, heads, R, E, full, float(stage[1]), hbm_peak, peak_src, stage)
+    roof["note"] = "three K-agg launches per step (levels 2, 1, 0); bytes and time summed; sparse levels gather the active rows only"
     finite = bool(torch.isfinite(out[:: max(n // 4096, 1)]).all().item())
     blk = {"config": "3-layer stacked forward across HNSW levels, 10M nodes d=128, 1 B200 (BASELINE configs[2])",
            "workload": f"{n} nodes d={d} M={m}, {heads} heads, 3 stacked layers over levels {levels} (edges {edges})",
@@ -400,8 +409,9 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
            "layer_node_updates_per_step": 3 * n, "edges_per_sec": E / (ms * 1e-3),
            "projection_mode": {0: "fp32_simt", 1: "fp32_3xtf32_tcgen05", 2: "tf32_tcgen05"}[mode],
            "roofline": roof,
-           "roofline_projections": gemm_roofline(d, d, heads, R, 3.0 * n, float(stage[0] + stage[2]), passes, hbm_peak,
-                                                 tf32_peak, tf32_src),
+           "rows_with_neighbours_per_level": active,
+           "roofline_projections": gemm_roofline(d, d, heads, R, full, float(stage[0] + stage[2]), passes, hbm_peak,
+                                                 tf32_peak, tf32_src, msg_only_rows=msg_only),
            "hbm_used_gb": h.mem_used_gb(), "output_finite_sampled": finite}
     for o in layers:
         o.close()
