@@ -8,7 +8,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libruvgnn.so"
-SOURCES = ["ffi.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc3.cu", "rowops.cu", "search.cu", "dist.cu", "store.cu", "json.cc", "packer.cc", "hnswio.cc"]
+SOURCES = ["ffi.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc3.cu", "gemm_upd_fused.cu", "rowops.cu", "search.cu", "dist.cu", "store.cu", "json.cc", "packer.cc", "hnswio.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -180,6 +180,24 @@ cudaError_t launch_validate_csr(const uint64_t *row_ptr, const uint32_t *col_idx
                                 uint64_t n_cols, uint64_t n_edges, int *d_flag, cudaStream_t s,
                                 uint64_t *launches);
 
+// ---- fused K-upd (gemm_upd_fused.cu, H = 128, tensor-core modes) ---------------------
+// out[row] = LayerNorm(deg(row) > 0 ? GRU(Wf [S | agg] + bf, m) * keep : m) for rows
+// [row_begin, row_begin + rows); every base pointer is indexed by the absolute row number.
+struct FusedUpdArgs {
+  int64_t rows = 0;
+  uint64_t row_begin = 0;
+  const float *A1 = nullptr;  // gather state [row][lda1]: S_0..S_{h-1} | agg (R = 1) or o | agg (R = 3)
+  int64_t lda1 = 0;
+  int32_t K1 = 0;  // (heads + 1) * 128 or 256
+  const float *m = nullptr;  // message rows
+  int64_t ldm = 0;
+  const float *bf = nullptr, *bzr = nullptr, *bh = nullptr, *gamma = nullptr, *beta = nullptr;
+  float eps = 1e-5f, keep = 1.f;
+  const uint64_t *row_ptr = nullptr;  // nullptr: every row has neighbours
+  const uint32_t *scatter = nullptr;  // row r is written to out[scatter[r]]
+  float *out = nullptr;               // [.][128]
+};
+
 // ---- search.cu: batched differentiable_search / hierarchical_forward pieces ---------
 cudaError_t launch_row_norms(const float *x, uint64_t rows, uint32_t dim, float *norms,
                              cudaStream_t s, uint64_t *launches);

@@ -80,6 +80,9 @@ struct ruvgnn_layer {
   bool r1 = false;
   float *Wqk = nullptr, *bqk = nullptr;  // [heads*H][H]: Qt_g = W_k[g]^T (W_q[g] m + b_q[g])
   float *Wov = nullptr, *bov = nullptr;  // [H][heads*H]: attn = sum_g (W_o[:,g] W_v[g]) S_g + W_o b_v + b_o
+  // fused K-upd (H = 128, tensor-core modes): bias of the folded first stage; the matrix is tc TC_W_F
+  float *bf = nullptr;
+  bool fused_upd = false;
   ruvgnn::TcWeights tc;  // split (hi/lo) copies for the tcgen05 path; empty unless usable
 };
 

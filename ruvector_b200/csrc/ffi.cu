@@ -346,6 +346,25 @@ static int32_t update_rows_io(ruvgnn_ctx *c, const ruvgnn_layer *L, const UpdIO 
   const int64_t rows = (int64_t)(re - rb);
   const float *m = io.m + rb * io.ldm;
   int32_t rc;
+  if (L->fused_upd && L->mode != RUVGNN_MODE_FP32_SIMT) {  // H = 128: the whole chain in one kernel
+    FusedUpdArgs f;
+    f.rows = rows;
+    f.row_begin = rb;
+    f.A1 = io.oa;
+    f.lda1 = L->r1 ? (int64_t)(L->heads + 1) * H : 2 * (int64_t)H;
+    f.K1 = (int32_t)f.lda1;
+    f.m = io.m;
+    f.ldm = io.ldm;
+    f.bf = L->bf; f.bzr = L->bzr; f.bh = L->bh; f.gamma = L->gamma; f.beta = L->beta;
+    f.eps = L->host.eps;
+    f.keep = 1.0f - L->host.dropout;
+    f.row_ptr = io.row_ptr;
+    f.scatter = io.scatter;
+    f.out = io.out;
+    RUVGNN_CUDA_TRY(tc::launch_upd_fused(f, L->tc, L->mode == RUVGNN_MODE_TF32, c->sm_count, c->stream,
+                                         &c->launches));
+    return RUVGNN_OK;
+  }
   if (!L->r1) {  // combined = W_o o + b_o + agg
     GemmArgs g;
     g.M = rows; g.N = (int32_t)H; g.K1 = (int32_t)H;
@@ -554,7 +573,9 @@ int32_t upload_layer(ruvgnn_layer *L) {
   const size_t nB = (size_t)H + 3 * H + H + H + 2 * H + H + 2 * H;
   // + room for the R = 1 folded matrices (2 * heads * H * H + biases), allocated when used
   const size_t nR1 = (H == 128 && L->heads <= 8) ? 2 * (size_t)L->heads * H * H + (size_t)L->heads * H + H + 16 : 0;
-  std::vector<float> blob(nW + nB + nR1 + 64, 0.f);
+  // + the fused K-upd's first-stage matrix [H][(heads + 1) H] (or [H][2H]) and its bias, H = 128 only
+  const size_t nF = H == 128 ? (size_t)(L->heads + 1) * H * H + 2 * (size_t)H * H + H + 16 : 0;
+  std::vector<float> blob(nW + nB + nR1 + nF + 64, 0.f);
   size_t off = 0;
   auto take = [&](size_t n) {
     float *p = blob.data() + off;
@@ -667,6 +688,35 @@ int32_t upload_layer(ruvgnn_layer *L) {
       bov[o] = (float)bsum;
     }
   }
+  // Fused K-upd (gemm_upd_fused.cu), H = 128: out-proj, combine and w_agg (layer.rs:159,407,408) are
+  // one linear map of the gather state, a = W_agg (W_o' S + b_o' + agg) + b_agg
+  //   = [W_agg W_o' | W_agg] [S | agg] + (W_agg b_o' + b_agg),
+  // with (W_o', b_o') = (W_ov, b_ov) over the per-head sums (R = 1) or (W_o, b_o) over o (R = 3).
+  // Products in double precision; P == 1, so the column order is the identity.
+  float *Wf = nullptr, *bf = nullptr;
+  uint32_t KF = 0;
+  if (H == 128 && L->fast) {
+    const float *Wo1 = L->r1 ? Wov : Wo, *bo1 = L->r1 ? bov : bo;
+    const uint32_t Ko = L->r1 ? L->heads * H : H;
+    KF = Ko + H;
+    Wf = take((size_t)H * KF);
+    bf = take(H);
+    std::vector<double> acc(Ko);
+    for (uint32_t o = 0; o < H; ++o) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      double bsum = (double)bagg[o];
+      for (uint32_t t = 0; t < H; ++t) {
+        const double wa = (double)Wagg[(size_t)o * H + t];
+        const float *src = Wo1 + (size_t)t * Ko;
+        for (uint32_t i = 0; i < Ko; ++i) acc[i] += wa * (double)src[i];
+        bsum += wa * (double)bo1[t];
+      }
+      float *row = Wf + (size_t)o * KF;
+      for (uint32_t i = 0; i < Ko; ++i) row[i] = (float)acc[i];
+      memcpy(row + Ko, Wagg + (size_t)o * H, sizeof(float) * H);
+      bf[o] = (float)bsum;
+    }
+  }
   RUVGNN_CUDA_TRY(cudaMalloc(&L->blob, blob.size() * sizeof(float)));
   RUVGNN_CUDA_TRY(
       cudaMemcpy(L->blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -682,14 +732,21 @@ int32_t upload_layer(ruvgnn_layer *L) {
     L->Wqk = dev(Wqk); L->bqk = dev(bqk);
     L->Wov = dev(Wov); L->bov = dev(bov);
   }
-  // tcgen05 path: split copies (hi/lo) of the six device weight matrices
+  if (Wf) L->bf = dev(bf);
+  // tcgen05 path: split copies (hi/lo) of the device weight matrices
   const float *mats[TC_W_COUNT] = {Wmsg, L->r1 ? Wqk : Wqkv, L->r1 ? Wov : Wo, Wagg, Wzr, Wh,
-                                   Wqkv + (size_t)H * H};
-  const uint32_t rows[TC_W_COUNT] = {H, L->r1 ? L->heads * H : 3 * H, H, H, 2 * H, H, 2 * H};
-  const uint32_t cols[TC_W_COUNT] = {D, H, L->r1 ? L->heads * H : H, H, 2 * H, 2 * H, H};
+                                   Wqkv + (size_t)H * H, Wf};
+  const uint32_t rows[TC_W_COUNT] = {H, L->r1 ? L->heads * H : 3 * H, H, H, 2 * H, H, 2 * H, Wf ? H : 0};
+  const uint32_t cols[TC_W_COUNT] = {D, H, L->r1 ? L->heads * H : H, H, 2 * H, 2 * H, H, KF};
   cudaError_t e = tc_weights_create(mats, rows, cols, &L->tc);
   if (e != cudaSuccess)
     return fail(RUVGNN_ERR_CUDA, std::string("tc_weights_create: ") + cudaGetErrorString(e));
+  {
+    // RUVGNN_FUSED_UPD=1 (read at layer creation): K-upd of an H = 128 layer as the one fused kernel
+    const char *fe = getenv("RUVGNN_FUSED_UPD");
+    const int want = fe ? atoi(fe) : 0;
+    L->fused_upd = want != 0 && Wf && tc::upd_fused_supported(L->tc, H);
+  }
   return RUVGNN_OK;
 }
 

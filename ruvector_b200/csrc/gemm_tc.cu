@@ -409,6 +409,7 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
   if (!encode) return cudaSuccess;  // driver too old for TMA descriptors: path stays unusable
   size_t total = 0;
   for (int i = 0; i < TC_W_COUNT; ++i) {
+    if (rows[i] == 0) continue;  // matrix not present for this layer shape
     if (cols[i] % 32 != 0 || pick_block_n(rows[i]) == 0) return cudaSuccess;
     total += 2 * (size_t)rows[i] * cols[i];
   }
@@ -418,7 +419,7 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
   size_t off = 0;
   size_t offs_hi[TC_W_COUNT], offs_lo[TC_W_COUNT];
   for (int i = 0; i < TC_W_COUNT; ++i) {
-    const size_t n = (size_t)rows[i] * cols[i];
+    const size_t n = (size_t)rows[i] * cols[i];  // 0 for an absent matrix
     offs_hi[i] = off;
     offs_lo[i] = off + n;
     for (size_t j = 0; j < n; ++j) {
@@ -444,6 +445,10 @@ cudaError_t tc_weights_create(const float *const host_mats[TC_W_COUNT],
     out->lo[i] = out->blob + offs_lo[i];
     out->rows[i] = rows[i];
     out->cols[i] = cols[i];
+    maps->block_n[i] = 0;
+    maps->block_n3[i] = 0;
+    maps->ts_ok[i] = false;
+    if (rows[i] == 0) continue;
     maps->block_n[i] = pick_block_n(rows[i]);
     const cuuint64_t dims[2] = {cols[i], rows[i]};
     const cuuint64_t strides[1] = {(cuuint64_t)cols[i] * sizeof(float)};

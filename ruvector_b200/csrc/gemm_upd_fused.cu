@@ -1,0 +1,510 @@
+// Fused K-upd for H = 128 (the config 1 / 3 / 5 layer shape): one tcgen05 kernel per row block
+// instead of four GEMMs and a LayerNorm launch.
+//
+//   a   = Wf [S | agg] + bf              Wf = [W_agg W_ov | W_agg] folded at layer creation
+//                                        (layer.rs:156-159 out-proj, :407 combine, :408 w_agg)
+//   z   = sigmoid(W_z a + U_z m + b)     (GRUCell::forward, layer.rs:255-275)
+//   rh  = sigmoid(W_r a + U_r m + b) * m
+//   d   = ((1 - z) m + z tanh(W_h a + U_h rh + b)) * (1 - p)      (:448-451 dropout scale)
+//   out = LayerNorm(deg > 0 ? d : m)     (:68-81, no-neighbour rows :385-389)
+//
+// A 128-row tile goes through all five stages inside one CTA; nothing between the gather state
+// and the output row touches HBM: per node the kernel reads (heads + 1) H floats of gather state
+// and the message row, and writes the output row once.
+//
+// How the chain stays on chip: tcgen05.mma accepts its A operand from TMEM (TS form) in the very
+// layout the accumulator has -- TMEM lane = tile row, column = k.  An epilogue thread owns one row:
+// it reads the accumulator (tcgen05.ld), applies bias / gate, splits the value into its TF32 part
+// and the exact remainder (3xTF32, gemm_tc.cu) and writes both back with tcgen05.st as the next
+// stage's A operand.  TMEM columns (512):
+//   X [  0,128)  accumulator of a, then z, then r
+//   Y [128,256)  ring of two streamed A k-blocks (hi | lo, 32 + 32 columns each): gather-state and
+//                message rows on their way from global memory; accumulator of the candidate GEMM
+//                once the ring has drained
+//   P [256,384)  resident A operand, TF32 part:  a, later rh
+//   Q [384,512)  resident A operand, remainder
+// z (later d) of the tile lives in shared memory, one private row per epilogue thread.
+//
+// Warp roles (as gemm_tc3.cu): warp 0 TMA weight producer, warp 1 MMA issuer, warps 2-5 A
+// producers (one tile row per thread), warps 6-9 epilogue.  Per tile the MMA warp runs
+//   S1 (K1/32 k-blocks, A streamed) | E1 | Z (a resident, m streamed) | Ez | R | C1 (a resident)
+//   | Er | C2 (rh resident) | E3
+// with the E phases on the epilogue warps.  Weight k-blocks keep streaming through the phases.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace ruvgnn {
+namespace tc {
+namespace {
+
+constexpr int BK = 32;
+constexpr int HF = 128;  // hidden size this kernel is written for
+constexpr uint32_t COL_X = 0, COL_Y = 128, COL_P = 256, COL_Q = 384;
+constexpr int A_STAGES = 2;
+constexpr int B_STAGES = 4;
+constexpr int B_TILE_BYTES = HF * BK * 4;  // one 128-row x 32-float weight k-block
+constexpr int B_STAGE_BYTES = 2 * B_TILE_BYTES;
+constexpr int ZLD = 132;  // floats per private z/d row: 16-byte aligned, conflict-free float4 access
+constexpr int NVEC = 6;   // bf | bz | br | bh | gamma | beta, 128 floats each
+
+struct FusedParams {
+  FusedUpdArgs a;
+  int single_pass;
+  int pf_dist;
+  int num_tiles;
+};
+
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+}
+__device__ __forceinline__ void ld_row32(const float *src, float4 (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[2 * i].x), "=f"(v[2 * i].y), "=f"(v[2 * i].z), "=f"(v[2 * i].w),
+                   "=f"(v[2 * i + 1].x), "=f"(v[2 * i + 1].y), "=f"(v[2 * i + 1].z),
+                   "=f"(v[2 * i + 1].w)
+                 : "l"(src + 8 * i));
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constant__ CUtensorMap mf_lo,
+                 const __grid_constant__ CUtensorMap mzr_hi, const __grid_constant__ CUtensorMap mzr_lo,
+                 const __grid_constant__ CUtensorMap mh_hi, const __grid_constant__ CUtensorMap mh_lo,
+                 const FusedParams q) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const FusedUpdArgs &a = q.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool single = q.single_pass != 0;
+
+  uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~(uintptr_t)1023);
+  auto b_hi = [&](int s) { return base + (size_t)s * B_STAGE_BYTES; };
+  auto b_lo = [&](int s) { return base + (size_t)s * B_STAGE_BYTES + B_TILE_BYTES; };
+  float *zrows = reinterpret_cast<float *>(base + (size_t)B_STAGES * B_STAGE_BYTES);
+  float *vecs = zrows + BLOCK_M * ZLD;
+  const float *s_bf = vecs, *s_bz = vecs + HF, *s_br = vecs + 2 * HF, *s_bh = vecs + 3 * HF;
+  const float *s_gamma = vecs + 4 * HF, *s_beta = vecs + 5 * HF;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(vecs + NVEC * HF);
+  uint64_t *full_b = bars, *empty_b = bars + B_STAGES;
+  uint64_t *full_a = bars + 2 * B_STAGES, *empty_a = full_a + A_STAGES;
+  uint64_t *acc_bar = empty_a + A_STAGES;  // MMA -> epilogue: an accumulator phase is complete
+  uint64_t *epi_bar = acc_bar + 1;         // epilogue -> MMA: the phase's results are in place
+  uint64_t *ring_free = acc_bar + 2;       // epilogue -> A producers: Y holds no accumulator any more
+  uint64_t *drain_bar = acc_bar + 3;       // MMA -> MMA: the MMAs that read the ring as A have completed
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_bar + 4);
+
+  for (int i = threadIdx.x; i < HF; i += NUM_THREADS) {
+    vecs[i] = a.bf[i];
+    vecs[HF + i] = a.bzr[i];
+    vecs[2 * HF + i] = a.bzr[HF + i];
+    vecs[3 * HF + i] = a.bh[i];
+    vecs[4 * HF + i] = a.gamma[i];
+    vecs[5 * HF + i] = a.beta[i];
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mf_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mf_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mzr_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mzr_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mh_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mh_lo)) : "memory");
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
+    }
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(&full_a[s], 4);  // one arrive per producer warp
+      mbar_init(&empty_a[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    mbar_init(epi_bar, 4);  // one arrive per epilogue warp
+    mbar_init(ring_free, 4);
+    mbar_init(drain_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int NK1 = a.K1 / BK;   // streamed k-blocks of stage 1
+  const int NA = NK1 + 8;      // A-ring k-blocks per tile: stage 1, then m for Z, m again for R
+  const int NB = NK1 + 24;     // weight k-blocks per tile: Wf, Wzr rows [0,128), rows [128,256), Wh
+  const int num_tiles = q.num_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer: the tile's weight k-blocks in the order the MMA warp consumes them =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int j = 0; j < NB; ++j) {
+          const CUtensorMap *mh, *ml;
+          int c0, c1 = 0;
+          if (j < NK1) {
+            mh = &mf_hi; ml = &mf_lo; c0 = j * BK;
+          } else if (j < NK1 + 16) {
+            const int jj = j - NK1;
+            mh = &mzr_hi; ml = &mzr_lo; c0 = (jj & 7) * BK; c1 = (jj >> 3) * HF;
+          } else {
+            mh = &mh_hi; ml = &mh_lo; c0 = (j - NK1 - 16) * BK;
+          }
+          mbar_wait(&empty_b[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_b[stage], single ? B_TILE_BYTES : 2 * B_TILE_BYTES);
+          tma_load_2d(b_hi(stage), mh, &full_b[stage], c0, c1);
+          if (!single) tma_load_2d(b_lo(stage), ml, &full_b[stage], c0, c1);
+          if (++stage == B_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(HF);
+      const uint32_t dX = tmem_base + COL_X, dY = tmem_base + COL_Y;
+      const uint32_t tP = tmem_base + COL_P, tQ = tmem_base + COL_Q;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0, pe = 0, pd = 0;
+      // one weight k-block against one A k-block (hi at ah, remainder at al)
+      auto kblock = [&](uint32_t d, uint32_t ah, uint32_t al, bool first_kb) {
+        mbar_wait(&full_b[sb], pb);
+        tc_fence_after();
+        const uint64_t bh = make_desc<BK>(smem_u32(b_hi(sb)));
+        const uint64_t bl = make_desc<BK>(smem_u32(b_lo(sb)));
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t off = (uint64_t)((kk * 32) >> 4);
+          const uint32_t acc = (first_kb && kk == 0) ? 0u : 1u;
+          if (single) {
+            umma_tf32_ts(d, ah + kk * 8, bh + off, idesc, acc);
+          } else {
+            umma_tf32_ts(d, al + kk * 8, bh + off, idesc, acc);
+            umma_tf32_ts(d, ah + kk * 8, bl + off, idesc, 1u);
+            umma_tf32_ts(d, ah + kk * 8, bh + off, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_b[sb]);
+        if (++sb == B_STAGES) {
+          sb = 0;
+          pb ^= 1;
+        }
+      };
+      auto ring_kblock = [&](uint32_t d, bool first_kb) {
+        mbar_wait(&full_a[sa], pa);
+        const uint32_t ah = tmem_base + COL_Y + (uint32_t)(sa * 64);
+        kblock(d, ah, ah + 32, first_kb);
+        umma_commit(&empty_a[sa]);
+        if (++sa == A_STAGES) {
+          sa = 0;
+          pa ^= 1;
+        }
+      };
+      auto wait_epilogue = [&]() {
+        mbar_wait(epi_bar, pe);
+        pe ^= 1;
+        tc_fence_after();
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < NK1; ++kb) ring_kblock(dX, kb == 0);  // S1: X = [S | agg] Wf^T
+        umma_commit(acc_bar);
+        for (int half = 0; half < 2; ++half) {  // Z, then R: X = [a | m] Wzr[half]^T
+          wait_epilogue();                      // E1: a in P | Q (half 0);  Ez: z taken out of X (half 1)
+          for (int kb = 0; kb < 4; ++kb) kblock(dX, tP + kb * 32, tQ + kb * 32, kb == 0);
+          for (int kb = 0; kb < 4; ++kb) ring_kblock(dX, false);
+          if (half == 0) umma_commit(acc_bar);
+        }
+        // C1: Y = a Wh[:, 0:128]^T.  Y was the A ring until here; the producers hold until ring_free, and
+        // the MMAs that read it as their A operand must have completed before another MMA writes it as
+        // its accumulator (only MMAs on the SAME accumulator are ordered by the pipeline itself).
+        umma_commit(drain_bar);
+        mbar_wait(drain_bar, pd);
+        pd ^= 1;
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb) kblock(dY, tP + kb * 32, tQ + kb * 32, kb == 0);
+        umma_commit(acc_bar);  // r complete in X, a no longer needed
+        wait_epilogue();       // Er: rh in P | Q
+        for (int kb = 0; kb < 4; ++kb) kblock(dY, tP + kb * 32, tQ + kb * 32, false);  // C2
+        umma_commit(acc_bar);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== A producers: one tile row per thread -> (hi, lo) -> TMEM ring =====
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t tiles_done = 0;
+    float4 cur[8], nxt[8];
+    auto src_of = [&](int tile, int i) -> const float * {
+      const int64_t r = (int64_t)tile * BLOCK_M + row_in_tile;
+      if (r >= a.rows) return nullptr;
+      const int64_t row = (int64_t)a.row_begin + r;
+      return i < NK1 ? a.A1 + row * a.lda1 + (int64_t)i * BK
+                     : a.m + row * a.ldm + (int64_t)((i - NK1) & 3) * BK;
+    };
+    auto issue = [&](float4 (&v)[8], int tile, int i) {
+      const float *src = src_of(tile, i);
+      if (src) {
+        ld_row32(src, v);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto prefetch_ahead = [&](int tile, int i) {
+      int t = tile, k = i + q.pf_dist;
+      while (k >= NA) {
+        k -= NA;
+        t += gridDim.x;
+      }
+      if (t >= num_tiles || k >= NK1 + 4) return;  // the second pass over m hits L2 anyway
+      const float *src = src_of(t, k);
+      if (src) prefetch_l2(src);
+    };
+    int tile = blockIdx.x, i = 0;
+    if (tile < num_tiles) issue(nxt, tile, 0);
+    if (q.pf_dist > 0 && tile < num_tiles)
+      for (int k = 1 - q.pf_dist; k < 0; ++k) prefetch_ahead(tile, k);
+    while (tile < num_tiles) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+      int ntile = tile, ni = i + 1;
+      if (ni == NA) {
+        ni = 0;
+        ntile = tile + gridDim.x;
+      }
+      if (ntile < num_tiles) issue(nxt, ntile, ni);
+      if (q.pf_dist > 0) prefetch_ahead(tile, i);
+      mbar_wait(&empty_a[stage], phase ^ 1);
+      // Y doubles as the candidate accumulator of the previous tile until its last epilogue has read it
+      if (i == 0 && tiles_done > 0) mbar_wait(ring_free, (tiles_done - 1) & 1);
+      tc_fence_after();
+      const uint32_t ah = tmem_base + lane_base + COL_Y + (uint32_t)(stage * 64);
+      uint32_t r[32];
+      const float *cf = reinterpret_cast<const float *>(cur);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) r[k] = tf32_bits(cf[k]);
+      tmem_st32(ah, r);
+      if (!single) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(cf[k] - __uint_as_float(r[k]));
+        tmem_st32(ah + 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[stage]);
+      if (++stage == A_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+      if (ni == 0) ++tiles_done;
+      tile = ntile;
+      i = ni;
+    }
+  } else {
+    // ===== epilogue warps: the phases between the GEMMs, one tile row per thread =====
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t tX = tmem_base + lane_base + COL_X, tY = tmem_base + lane_base + COL_Y;
+    const uint32_t tP = tmem_base + lane_base + COL_P, tQ = tmem_base + lane_base + COL_Q;
+    float *zrow = zrows + row_in_tile * ZLD;
+    const float4 g4 = reinterpret_cast<const float4 *>(s_gamma)[lane];
+    const float4 b4 = reinterpret_cast<const float4 *>(s_beta)[lane];
+    uint32_t pacc = 0;
+    auto wait_acc = [&]() {
+      mbar_wait(acc_bar, pacc);
+      pacc ^= 1;
+      tc_fence_after();
+    };
+    auto signal = [&](uint64_t *bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // v -> A operand columns [c, c + 32) of P | Q
+    auto store_operand = [&](int c, const float (&v)[32]) {
+      uint32_t r[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = tf32_bits(v[j]);
+      tmem_st32(tP + (uint32_t)c, r);
+      if (!single) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j] - __uint_as_float(r[j]));
+        tmem_st32(tQ + (uint32_t)c, r);
+      }
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t r_local = (int64_t)tile * BLOCK_M + row_in_tile;
+      const bool valid = r_local < a.rows;
+      const int64_t row = (int64_t)a.row_begin + r_local;
+      const int64_t row0 = row - lane;  // first row of this warp's 32-row slab
+      const float *mrow = a.m + (valid ? row : (int64_t)a.row_begin) * a.ldm;
+      const bool iso = valid && a.row_ptr && a.row_ptr[row] == a.row_ptr[row + 1];
+
+      // ---- E1: a = acc + bf  ->  P | Q
+      wait_acc();
+#pragma unroll 1
+      for (int c = 0; c < HF; c += 32) {
+        float v[32];
+        tmem_ld32(tX + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += s_bf[c + j];
+        store_operand(c, v);
+      }
+      tmem_st_wait();
+      signal(epi_bar);
+
+      // ---- Ez: z = sigmoid(acc + b_z)  ->  private shared row
+      wait_acc();
+#pragma unroll 1
+      for (int c = 0; c < HF; c += 32) {
+        float v[32];
+        tmem_ld32(tX + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 z;
+          z.x = sigmoid_ref(v[4 * j + 0] + s_bz[c + 4 * j + 0]);
+          z.y = sigmoid_ref(v[4 * j + 1] + s_bz[c + 4 * j + 1]);
+          z.z = sigmoid_ref(v[4 * j + 2] + s_bz[c + 4 * j + 2]);
+          z.w = sigmoid_ref(v[4 * j + 3] + s_bz[c + 4 * j + 3]);
+          *reinterpret_cast<float4 *>(zrow + c + 4 * j) = z;
+        }
+      }
+      signal(epi_bar);
+
+      // ---- Er: rh = sigmoid(acc + b_r) * m  ->  P | Q   (a is dead: C1 has completed)
+      wait_acc();
+#pragma unroll 1
+      for (int c = 0; c < HF; c += 32) {
+        float4 mm[8];
+        ld_row32(mrow + c, mm);
+        float v[32];
+        tmem_ld32(tX + (uint32_t)c, v);
+        const float *mf = reinterpret_cast<const float *>(mm);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sigmoid_ref(v[j] + s_br[c + j]) * mf[j];
+        store_operand(c, v);
+      }
+      tmem_st_wait();
+      signal(epi_bar);
+
+      // ---- E3: d = ((1 - z) m + z tanh(acc + b_h)) * keep, LayerNorm, store
+      wait_acc();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < HF; c += 32) {
+        float4 mm[8];
+        ld_row32(mrow + c, mm);
+        float v[32];
+        tmem_ld32(tY + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 z = *reinterpret_cast<const float4 *>(zrow + c + 4 * j);
+          const float4 m = mm[j];
+          float4 d;
+          d.x = ((1.0f - z.x) * m.x + z.x * tanh_ref(v[4 * j + 0] + s_bh[c + 4 * j + 0])) * a.keep;
+          d.y = ((1.0f - z.y) * m.y + z.y * tanh_ref(v[4 * j + 1] + s_bh[c + 4 * j + 1])) * a.keep;
+          d.z = ((1.0f - z.z) * m.z + z.z * tanh_ref(v[4 * j + 2] + s_bh[c + 4 * j + 2])) * a.keep;
+          d.w = ((1.0f - z.w) * m.w + z.w * tanh_ref(v[4 * j + 3] + s_bh[c + 4 * j + 3])) * a.keep;
+          if (iso) d = m;  // no neighbours: LN(W_msg x + b), layer.rs:385-389
+          sum += (d.x + d.y) + (d.z + d.w);
+          *reinterpret_cast<float4 *>(zrow + c + 4 * j) = d;
+        }
+      }
+      signal(ring_free);  // Y has been read: the producers may stream the next tile into it
+      const float mean = sum * (1.0f / HF);
+      float var = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < HF / 4; ++j) {
+        const float4 d = *reinterpret_cast<const float4 *>(zrow + 4 * j);
+        const float dx = d.x - mean, dy = d.y - mean, dz = d.z - mean, dw = d.w - mean;
+        var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, var))));
+      }
+      const float denom = sqrtf(var * (1.0f / HF) + a.eps);
+      uint64_t dst_row = valid ? (a.scatter ? (uint64_t)a.scatter[row] : (uint64_t)row) : 0;
+      __syncwarp();  // the slab's d rows are visible to the whole warp
+      // one warp instruction reads one row of the slab (512 contiguous bytes) and writes it coalesced
+      const float *slab = zrows + (quad * 32) * ZLD;
+      const int64_t rows_left = a.rows - ((int64_t)tile * BLOCK_M + quad * 32);
+      const int nrows = rows_left > 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
+      (void)row0;
+      for (int r = 0; r < nrows; ++r) {
+        const float mu = __shfl_sync(0xffffffffu, mean, r);
+        const float dn = __shfl_sync(0xffffffffu, denom, r);
+        const uint64_t dr = __shfl_sync(0xffffffffu, dst_row, r);
+        const float4 x = *reinterpret_cast<const float4 *>(slab + r * ZLD + 4 * lane);
+        float4 o;
+        o.x = g4.x * ((x.x - mu) / dn) + b4.x;
+        o.y = g4.y * ((x.y - mu) / dn) + b4.y;
+        o.z = g4.z * ((x.z - mu) / dn) + b4.z;
+        o.w = g4.w * ((x.w - mu) / dn) + b4.w;
+        *reinterpret_cast<float4 *>(a.out + dr * (uint64_t)HF + 4 * lane) = o;
+      }
+      __syncwarp();  // before the next tile's Ez overwrites the slab
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr size_t kFusedSmem = 1024 + (size_t)B_STAGES * B_STAGE_BYTES +
+                              (size_t)BLOCK_M * ZLD * sizeof(float) + NVEC * HF * sizeof(float) + 256;
+static_assert(kFusedSmem <= 227 * 1024, "fused K-upd shared memory");
+
+}  // namespace
+
+bool upd_fused_supported(const TcWeights &w, uint32_t H) {
+  const TcMaps *maps = static_cast<const TcMaps *>(w.tmaps);
+  if (!w.usable || !maps || H != (uint32_t)HF) return false;
+  const int ids[3] = {TC_W_F, TC_W_ZR, TC_W_H};
+  for (int i : ids)
+    if (!maps->ts_ok[i] || maps->block_n3[i] != HF) return false;
+  return w.rows[TC_W_F] == (uint32_t)HF && w.cols[TC_W_F] % BK == 0 && w.rows[TC_W_ZR] == 2u * HF &&
+         w.cols[TC_W_ZR] == 2u * HF && w.rows[TC_W_H] == (uint32_t)HF && w.cols[TC_W_H] == 2u * HF;
+}
+
+cudaError_t launch_upd_fused(const FusedUpdArgs &a, const TcWeights &w, bool single_pass, int sm_count,
+                             cudaStream_t s, uint64_t *launches) {
+  if (a.rows <= 0) return cudaSuccess;
+  if (!upd_fused_supported(w, HF) || (uint32_t)a.K1 != w.cols[TC_W_F]) return cudaErrorInvalidValue;
+  const TcMaps *maps = static_cast<const TcMaps *>(w.tmaps);
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool &configured = configured_dev[dev & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(upd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kFusedSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  FusedParams q;
+  q.a = a;
+  q.single_pass = single_pass ? 1 : 0;
+  q.pf_dist = tc_pf_dist();
+  const int64_t tiles = (a.rows + BLOCK_M - 1) / BLOCK_M;
+  q.num_tiles = (int)tiles;
+  const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+  if (launches) ++*launches;
+  upd_fused_kernel<<<grid, NUM_THREADS, kFusedSmem, s>>>(maps->hi3[TC_W_F], maps->lo3[TC_W_F],
+                                                         maps->hi3[TC_W_ZR], maps->lo3[TC_W_ZR],
+                                                         maps->hi3[TC_W_H], maps->lo3[TC_W_H], q);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace ruvgnn
