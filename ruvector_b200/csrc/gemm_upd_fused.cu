@@ -53,6 +53,8 @@ struct FusedParams {
   int single_pass;
   int pf_dist;
   int num_tiles;
+  int debug;  // timing experiments only (RUVGNN_FUSED_DEBUG): 1 = no A loads, 2 = no weight TMA, 4 = no MMAs,
+              // 8 = no activation math / message loads in the epilogues.  Results are garbage.
 };
 
 __device__ __forceinline__ uint32_t tf32_bits(float x) {
@@ -153,9 +155,13 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
             mh = &mh_hi; ml = &mh_lo; c0 = (j - NK1 - 16) * BK;
           }
           mbar_wait(&empty_b[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_b[stage], single ? B_TILE_BYTES : 2 * B_TILE_BYTES);
-          tma_load_2d(b_hi(stage), mh, &full_b[stage], c0, c1);
-          if (!single) tma_load_2d(b_lo(stage), ml, &full_b[stage], c0, c1);
+          if (q.debug & 2) {
+            mbar_arrive(&full_b[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_b[stage], single ? B_TILE_BYTES : 2 * B_TILE_BYTES);
+            tma_load_2d(b_hi(stage), mh, &full_b[stage], c0, c1);
+            if (!single) tma_load_2d(b_lo(stage), ml, &full_b[stage], c0, c1);
+          }
           if (++stage == B_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -181,7 +187,8 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         for (int kk = 0; kk < BK / 8; ++kk) {
           const uint64_t off = (uint64_t)((kk * 32) >> 4);
           const uint32_t acc = (first_kb && kk == 0) ? 0u : 1u;
-          if (single) {
+          if (q.debug & 4) {
+          } else if (single) {
             umma_tf32_ts(d, ah + kk * 8, bh + off, idesc, acc);
           } else {
             umma_tf32_ts(d, al + kk * 8, bh + off, idesc, acc);
@@ -251,7 +258,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
     };
     auto issue = [&](float4 (&v)[8], int tile, int i) {
       const float *src = src_of(tile, i);
-      if (src) {
+      if (src && !(q.debug & 1)) {
         ld_row32(src, v);
       } else {
 #pragma unroll
@@ -346,7 +353,6 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       const int64_t r_local = (int64_t)tile * BLOCK_M + row_in_tile;
       const bool valid = r_local < a.rows;
       const int64_t row = (int64_t)a.row_begin + r_local;
-      const int64_t row0 = row - lane;  // first row of this warp's 32-row slab
       const float *mrow = a.m + (valid ? row : (int64_t)a.row_begin) * a.ldm;
       const bool iso = valid && a.row_ptr && a.row_ptr[row] == a.row_ptr[row + 1];
 
@@ -369,6 +375,12 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       for (int c = 0; c < HF; c += 32) {
         float v[32];
         tmem_ld32(tX + (uint32_t)c, v);
+        if (q.debug & 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4 *>(zrow + c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 z;
@@ -385,9 +397,14 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       wait_acc();
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
+        float v[32];
+        if (q.debug & 8) {
+          tmem_ld32(tX + (uint32_t)c, v);
+          store_operand(c, v);
+          continue;
+        }
         float4 mm[8];
         ld_row32(mrow + c, mm);
-        float v[32];
         tmem_ld32(tX + (uint32_t)c, v);
         const float *mf = reinterpret_cast<const float *>(mm);
 #pragma unroll
@@ -399,12 +416,18 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
 
       // ---- E3: d = ((1 - z) m + z tanh(acc + b_h)) * keep, LayerNorm, store
       wait_acc();
-      float sum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
+        float v[32];
+        if (q.debug & 8) {
+          tmem_ld32(tY + (uint32_t)c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4 *>(zrow + c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          continue;
+        }
         float4 mm[8];
         ld_row32(mrow + c, mm);
-        float v[32];
         tmem_ld32(tY + (uint32_t)c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -416,38 +439,37 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
           d.z = ((1.0f - z.z) * m.z + z.z * tanh_ref(v[4 * j + 2] + s_bh[c + 4 * j + 2])) * a.keep;
           d.w = ((1.0f - z.w) * m.w + z.w * tanh_ref(v[4 * j + 3] + s_bh[c + 4 * j + 3])) * a.keep;
           if (iso) d = m;  // no neighbours: LN(W_msg x + b), layer.rs:385-389
-          sum += (d.x + d.y) + (d.z + d.w);
           *reinterpret_cast<float4 *>(zrow + c + 4 * j) = d;
         }
       }
       signal(ring_free);  // Y has been read: the producers may stream the next tile into it
-      const float mean = sum * (1.0f / HF);
-      float var = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < HF / 4; ++j) {
-        const float4 d = *reinterpret_cast<const float4 *>(zrow + 4 * j);
-        const float dx = d.x - mean, dy = d.y - mean, dz = d.z - mean, dw = d.w - mean;
-        var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, var))));
-      }
-      const float denom = sqrtf(var * (1.0f / HF) + a.eps);
-      uint64_t dst_row = valid ? (a.scatter ? (uint64_t)a.scatter[row] : (uint64_t)row) : 0;
+      const uint64_t dst_row = valid ? (a.scatter ? (uint64_t)a.scatter[row] : (uint64_t)row) : 0;
       __syncwarp();  // the slab's d rows are visible to the whole warp
-      // one warp instruction reads one row of the slab (512 contiguous bytes) and writes it coalesced
+      // LayerNorm, one row of the slab per warp instruction: lane l holds floats [4l, 4l + 4) of the row,
+      // the row is read from shared memory and written to global memory as 512 contiguous bytes.  Same
+      // arithmetic, in the same order, as layernorm_fast_kernel<1> (rowops.cu), so the rows this kernel
+      // normalises carry the bits that kernel would give them (sparse levels mix the two).
       const float *slab = zrows + (quad * 32) * ZLD;
       const int64_t rows_left = a.rows - ((int64_t)tile * BLOCK_M + quad * 32);
       const int nrows = rows_left > 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
-      (void)row0;
       for (int r = 0; r < nrows; ++r) {
-        const float mu = __shfl_sync(0xffffffffu, mean, r);
-        const float dn = __shfl_sync(0xffffffffu, denom, r);
         const uint64_t dr = __shfl_sync(0xffffffffu, dst_row, r);
-        const float4 x = *reinterpret_cast<const float4 *>(slab + r * ZLD + 4 * lane);
-        float4 o;
-        o.x = g4.x * ((x.x - mu) / dn) + b4.x;
-        o.y = g4.y * ((x.y - mu) / dn) + b4.y;
-        o.z = g4.z * ((x.z - mu) / dn) + b4.z;
-        o.w = g4.w * ((x.w - mu) / dn) + b4.w;
-        *reinterpret_cast<float4 *>(a.out + dr * (uint64_t)HF + 4 * lane) = o;
+        float4 x = *reinterpret_cast<const float4 *>(slab + r * ZLD + 4 * lane);
+        float sum = (x.x + x.y) + (x.z + x.w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / HF);
+        x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+        float var = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, 0.f))));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float denom = sqrtf(var * (1.0f / HF) + a.eps);
+        float4 o4;
+        o4.x = g4.x * (x.x / denom) + b4.x;
+        o4.y = g4.y * (x.y / denom) + b4.y;
+        o4.z = g4.z * (x.z / denom) + b4.z;
+        o4.w = g4.w * (x.w / denom) + b4.w;
+        *reinterpret_cast<float4 *>(a.out + dr * (uint64_t)HF + 4 * lane) = o4;
       }
       __syncwarp();  // before the next tile's Ez overwrites the slab
     }
@@ -496,6 +518,14 @@ cudaError_t launch_upd_fused(const FusedUpdArgs &a, const TcWeights &w, bool sin
   q.a = a;
   q.single_pass = single_pass ? 1 : 0;
   q.pf_dist = tc_pf_dist();
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char *e = getenv("RUVGNN_FUSED_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    q.debug = dbg;
+  }
   const int64_t tiles = (a.rows + BLOCK_M - 1) / BLOCK_M;
   q.num_tiles = (int)tiles;
   const int grid = (int)(tiles < sm_count ? tiles : sm_count);
