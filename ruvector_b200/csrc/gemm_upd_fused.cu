@@ -18,18 +18,21 @@
 // and the exact remainder (3xTF32, gemm_tc.cu) and writes both back with tcgen05.st as the next
 // stage's A operand.  TMEM columns (512):
 //   X [  0,128)  accumulator of a, then z, then r
-//   Y [128,256)  ring of two streamed A k-blocks (hi | lo, 32 + 32 columns each): gather-state and
-//                message rows on their way from global memory; accumulator of the candidate GEMM
-//                once the ring has drained
-//   P [256,384)  resident A operand, TF32 part:  a, later rh
-//   Q [384,512)  resident A operand, remainder
+//   Y [128,256)  ring of two streamed message-row k-blocks (hi | lo, 32 + 32 columns each) during the gate
+//                GEMMs; accumulator of the candidate GEMM once that ring has drained
+//   P [256,384)  resident A operand, TF32 part:  a, later rh  } during stage 1, before a exists: ring of
+//   Q [384,512)  resident A operand, remainder               } four streamed gather-state k-blocks
 // z (later d) of the tile lives in shared memory, one private row per epilogue thread.
+// Stage 1 of tile n+1 touches X and P | Q only, so it runs under the last epilogue (candidate
+// activation, LayerNorm, output store) of tile n, which reads Y.
 //
 // Warp roles (as gemm_tc3.cu): warp 0 TMA weight producer, warp 1 MMA issuer, warps 2-5 A
 // producers (one tile row per thread), warps 6-9 epilogue.  Per tile the MMA warp runs
 //   S1 (K1/32 k-blocks, A streamed) | E1 | Z (a resident, m streamed) | Ez | R | C1 (a resident)
 //   | Er | C2 (rh resident) | E3
-// with the E phases on the epilogue warps.  Weight k-blocks keep streaming through the phases.
+// with the E phases on the epilogue warps.  Weight k-blocks keep streaming through the phases.  In Z
+// and R the resident and the streamed k-blocks alternate (a0 m0 a1 m1 ..), so a ring slot has two
+// k-blocks of MMA time to be refilled.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -41,7 +44,8 @@ namespace {
 constexpr int BK = 32;
 constexpr int HF = 128;  // hidden size this kernel is written for
 constexpr uint32_t COL_X = 0, COL_Y = 128, COL_P = 256, COL_Q = 384;
-constexpr int A_STAGES = 2;
+constexpr int S_STAGES = 4;  // stage-1 ring (in P | Q)
+constexpr int M_STAGES = 2;  // message-row ring (in Y)
 constexpr int B_STAGES = 4;
 constexpr int B_TILE_BYTES = HF * BK * 4;  // one 128-row x 32-float weight k-block
 constexpr int B_STAGE_BYTES = 2 * B_TILE_BYTES;
@@ -90,12 +94,14 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
   const float *s_gamma = vecs + 4 * HF, *s_beta = vecs + 5 * HF;
   uint64_t *bars = reinterpret_cast<uint64_t *>(vecs + NVEC * HF);
   uint64_t *full_b = bars, *empty_b = bars + B_STAGES;
-  uint64_t *full_a = bars + 2 * B_STAGES, *empty_a = full_a + A_STAGES;
-  uint64_t *acc_bar = empty_a + A_STAGES;  // MMA -> epilogue: an accumulator phase is complete
+  uint64_t *full_s = bars + 2 * B_STAGES, *empty_s = full_s + S_STAGES;
+  uint64_t *full_m = empty_s + S_STAGES, *empty_m = full_m + M_STAGES;
+  uint64_t *acc_bar = empty_m + M_STAGES;  // MMA -> epilogue: an accumulator phase is complete
   uint64_t *epi_bar = acc_bar + 1;         // epilogue -> MMA: the phase's results are in place
   uint64_t *ring_free = acc_bar + 2;       // epilogue -> A producers: Y holds no accumulator any more
-  uint64_t *drain_bar = acc_bar + 3;       // MMA -> MMA: the MMAs that read the ring as A have completed
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_bar + 4);
+  uint64_t *drain_bar = acc_bar + 3;       // MMA -> MMA: the MMAs that read the Y ring as A have completed
+  uint64_t *pq_free = acc_bar + 4;         // MMA -> A producers: the last MMAs reading rh from P | Q have completed
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_bar + 5);
 
   for (int i = threadIdx.x; i < HF; i += NUM_THREADS) {
     vecs[i] = a.bf[i];
@@ -116,14 +122,19 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       mbar_init(&full_b[s], 1);
       mbar_init(&empty_b[s], 1);
     }
-    for (int s = 0; s < A_STAGES; ++s) {
-      mbar_init(&full_a[s], 4);  // one arrive per producer warp
-      mbar_init(&empty_a[s], 1);
+    for (int s = 0; s < S_STAGES; ++s) {
+      mbar_init(&full_s[s], 4);  // one arrive per producer warp
+      mbar_init(&empty_s[s], 1);
+    }
+    for (int s = 0; s < M_STAGES; ++s) {
+      mbar_init(&full_m[s], 4);
+      mbar_init(&empty_m[s], 1);
     }
     mbar_init(acc_bar, 1);
     mbar_init(epi_bar, 4);  // one arrive per epilogue warp
     mbar_init(ring_free, 4);
     mbar_init(drain_bar, 1);
+    mbar_init(pq_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -149,8 +160,8 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
           if (j < NK1) {
             mh = &mf_hi; ml = &mf_lo; c0 = j * BK;
           } else if (j < NK1 + 16) {
-            const int jj = j - NK1;
-            mh = &mzr_hi; ml = &mzr_lo; c0 = (jj & 7) * BK; c1 = (jj >> 3) * HF;
+            const int jj = j - NK1, t = jj & 7;  // a0 m0 a1 m1 a2 m2 a3 m3: k-blocks 0 4 1 5 2 6 3 7
+            mh = &mzr_hi; ml = &mzr_lo; c0 = ((t >> 1) + (t & 1) * 4) * BK; c1 = (jj >> 3) * HF;
           } else {
             mh = &mh_hi; ml = &mh_lo; c0 = (j - NK1 - 16) * BK;
           }
@@ -175,8 +186,8 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       const uint32_t idesc = make_idesc_tf32(HF);
       const uint32_t dX = tmem_base + COL_X, dY = tmem_base + COL_Y;
       const uint32_t tP = tmem_base + COL_P, tQ = tmem_base + COL_Q;
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0, pe = 0, pd = 0;
+      int ss = 0, sm = 0, sb = 0;
+      uint32_t ps = 0, pm = 0, pb = 0, pe = 0, pd = 0;
       // one weight k-block against one A k-block (hi at ah, remainder at al)
       auto kblock = [&](uint32_t d, uint32_t ah, uint32_t al, bool first_kb) {
         mbar_wait(&full_b[sb], pb);
@@ -202,14 +213,24 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
           pb ^= 1;
         }
       };
-      auto ring_kblock = [&](uint32_t d, bool first_kb) {
-        mbar_wait(&full_a[sa], pa);
-        const uint32_t ah = tmem_base + COL_Y + (uint32_t)(sa * 64);
+      auto s_kblock = [&](uint32_t d, bool first_kb) {  // next slot of the stage-1 ring
+        mbar_wait(&full_s[ss], ps);
+        const uint32_t ah = tmem_base + COL_P + (uint32_t)(ss * 64);
         kblock(d, ah, ah + 32, first_kb);
-        umma_commit(&empty_a[sa]);
-        if (++sa == A_STAGES) {
-          sa = 0;
-          pa ^= 1;
+        umma_commit(&empty_s[ss]);
+        if (++ss == S_STAGES) {
+          ss = 0;
+          ps ^= 1;
+        }
+      };
+      auto m_kblock = [&](uint32_t d) {  // next slot of the message-row ring
+        mbar_wait(&full_m[sm], pm);
+        const uint32_t ah = tmem_base + COL_Y + (uint32_t)(sm * 64);
+        kblock(d, ah, ah + 32, false);
+        umma_commit(&empty_m[sm]);
+        if (++sm == M_STAGES) {
+          sm = 0;
+          pm ^= 1;
         }
       };
       auto wait_epilogue = [&]() {
@@ -218,17 +239,19 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         tc_fence_after();
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < NK1; ++kb) ring_kblock(dX, kb == 0);  // S1: X = [S | agg] Wf^T
+        for (int kb = 0; kb < NK1; ++kb) s_kblock(dX, kb == 0);  // S1: X = [S | agg] Wf^T
         umma_commit(acc_bar);
         for (int half = 0; half < 2; ++half) {  // Z, then R: X = [a | m] Wzr[half]^T
           wait_epilogue();                      // E1: a in P | Q (half 0);  Ez: z taken out of X (half 1)
-          for (int kb = 0; kb < 4; ++kb) kblock(dX, tP + kb * 32, tQ + kb * 32, kb == 0);
-          for (int kb = 0; kb < 4; ++kb) ring_kblock(dX, false);
+          for (int kb = 0; kb < 4; ++kb) {
+            kblock(dX, tP + kb * 32, tQ + kb * 32, kb == 0);
+            m_kblock(dX);
+          }
           if (half == 0) umma_commit(acc_bar);
         }
-        // C1: Y = a Wh[:, 0:128]^T.  Y was the A ring until here; the producers hold until ring_free, and
-        // the MMAs that read it as their A operand must have completed before another MMA writes it as
-        // its accumulator (only MMAs on the SAME accumulator are ordered by the pipeline itself).
+        // C1: Y = a Wh[:, 0:128]^T.  Y was the message-row ring until here; the producers hold until
+        // ring_free, and the MMAs that read it as their A operand must have completed before another MMA
+        // writes it as its accumulator (only MMAs on the SAME accumulator are ordered by the pipeline).
         umma_commit(drain_bar);
         mbar_wait(drain_bar, pd);
         pd ^= 1;
@@ -238,6 +261,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         wait_epilogue();       // Er: rh in P | Q
         for (int kb = 0; kb < 4; ++kb) kblock(dY, tP + kb * 32, tQ + kb * 32, false);  // C2
         umma_commit(acc_bar);
+        umma_commit(pq_free);  // the next tile's gather-state k-blocks may stream into P | Q
       }
     }
   } else if (warp < 6) {
@@ -245,8 +269,8 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    int stage = 0;
-    uint32_t phase = 0;
+    int ss = 0, sm = 0;
+    uint32_t ps = 0, pm = 0;
     uint32_t tiles_done = 0;
     float4 cur[8], nxt[8];
     auto src_of = [&](int tile, int i) -> const float * {
@@ -289,11 +313,32 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       }
       if (ntile < num_tiles) issue(nxt, ntile, ni);
       if (q.pf_dist > 0) prefetch_ahead(tile, i);
-      mbar_wait(&empty_a[stage], phase ^ 1);
-      // Y doubles as the candidate accumulator of the previous tile until its last epilogue has read it
-      if (i == 0 && tiles_done > 0) mbar_wait(ring_free, (tiles_done - 1) & 1);
+      // Both rings live in columns that hold something else at the end of the previous tile: P | Q the
+      // candidate GEMM's rh operand (until its last MMAs have completed), Y its accumulator (until the last
+      // epilogue has read it).
+      uint64_t *full;
+      uint32_t col;
+      if (i < NK1) {
+        mbar_wait(&empty_s[ss], ps ^ 1);
+        if (i == 0 && tiles_done > 0) mbar_wait(pq_free, (tiles_done - 1) & 1);
+        full = &full_s[ss];
+        col = COL_P + (uint32_t)(ss * 64);
+        if (++ss == S_STAGES) {
+          ss = 0;
+          ps ^= 1;
+        }
+      } else {
+        mbar_wait(&empty_m[sm], pm ^ 1);
+        if (i == NK1 && tiles_done > 0) mbar_wait(ring_free, (tiles_done - 1) & 1);
+        full = &full_m[sm];
+        col = COL_Y + (uint32_t)(sm * 64);
+        if (++sm == M_STAGES) {
+          sm = 0;
+          pm ^= 1;
+        }
+      }
       tc_fence_after();
-      const uint32_t ah = tmem_base + lane_base + COL_Y + (uint32_t)(stage * 64);
+      const uint32_t ah = tmem_base + lane_base + col;
       uint32_t r[32];
       const float *cf = reinterpret_cast<const float *>(cur);
 #pragma unroll
@@ -307,11 +352,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_a[stage]);
-      if (++stage == A_STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
+      if (lane == 0) mbar_arrive(full);
       if (ni == 0) ++tiles_done;
       tile = ntile;
       i = ni;
@@ -442,7 +483,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
           *reinterpret_cast<float4 *>(zrow + c + 4 * j) = d;
         }
       }
-      signal(ring_free);  // Y has been read: the producers may stream the next tile into it
+      signal(ring_free);  // Y has been read: the producers may stream the next tile's message rows into it
       const uint64_t dst_row = valid ? (a.scatter ? (uint64_t)a.scatter[row] : (uint64_t)row) : 0;
       __syncwarp();  // the slab's d rows are visible to the whole warp
       // LayerNorm, one row of the slab per warp instruction: lane l holds floats [4l, 4l + 4) of the row,
