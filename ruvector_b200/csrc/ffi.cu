@@ -742,9 +742,10 @@ int32_t upload_layer(ruvgnn_layer *L) {
   if (e != cudaSuccess)
     return fail(RUVGNN_ERR_CUDA, std::string("tc_weights_create: ") + cudaGetErrorString(e));
   {
-    // RUVGNN_FUSED_UPD=1 (read at layer creation): K-upd of an H = 128 layer as the one fused kernel
+    // K-upd of an H = 128 layer runs as the one fused kernel (gemm_upd_fused.cu) in the tensor-core modes;
+    // RUVGNN_FUSED_UPD=0 (read at layer creation) keeps the four GEMMs + LayerNorm (A/B experiments).
     const char *fe = getenv("RUVGNN_FUSED_UPD");
-    const int want = fe ? atoi(fe) : 0;
+    const int want = fe ? atoi(fe) : 1;
     L->fused_upd = want != 0 && Wf && tc::upd_fused_supported(L->tc, H);
   }
   return RUVGNN_OK;

@@ -33,6 +33,7 @@
 // with the E phases on the epilogue warps.  Weight k-blocks keep streaming through the phases.  In Z
 // and R the resident and the streamed k-blocks alternate (a0 m0 a1 m1 ..), so a ring slot has two
 // k-blocks of MMA time to be refilled.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -59,7 +60,13 @@ struct FusedParams {
   int num_tiles;
   int debug;  // timing experiments only (RUVGNN_FUSED_DEBUG): 1 = no A loads, 2 = no weight TMA, 4 = no MMAs,
               // 8 = no activation math / message loads in the epilogues.  Results are garbage.
+              // 16 = phase timeline of CTA 0's third tile (clock64) into `trace`, printed by the launcher.
+  unsigned long long *trace;
 };
+
+__device__ __forceinline__ void trace_at(const FusedParams &q, bool on, int slot) {
+  if (on) q.trace[slot] = (unsigned long long)clock64();
+}
 
 __device__ __forceinline__ uint32_t tf32_bits(float x) {
   return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
@@ -239,15 +246,20 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         tc_fence_after();
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool tr = (q.debug & 16) && tile == 2 * (int)gridDim.x;
+        trace_at(q, tr, 0);
         for (int kb = 0; kb < NK1; ++kb) s_kblock(dX, kb == 0);  // S1: X = [S | agg] Wf^T
         umma_commit(acc_bar);
+        trace_at(q, tr, 1);
         for (int half = 0; half < 2; ++half) {  // Z, then R: X = [a | m] Wzr[half]^T
           wait_epilogue();                      // E1: a in P | Q (half 0);  Ez: z taken out of X (half 1)
+          trace_at(q, tr, 2 + 2 * half);
           for (int kb = 0; kb < 4; ++kb) {
             kblock(dX, tP + kb * 32, tQ + kb * 32, kb == 0);
             m_kblock(dX);
           }
           if (half == 0) umma_commit(acc_bar);
+          trace_at(q, tr, 3 + 2 * half);
         }
         // C1: Y = a Wh[:, 0:128]^T.  Y was the message-row ring until here; the producers hold until
         // ring_free, and the MMAs that read it as their A operand must have completed before another MMA
@@ -256,11 +268,15 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         mbar_wait(drain_bar, pd);
         pd ^= 1;
         tc_fence_after();
+        trace_at(q, tr, 6);
         for (int kb = 0; kb < 4; ++kb) kblock(dY, tP + kb * 32, tQ + kb * 32, kb == 0);
         umma_commit(acc_bar);  // r complete in X, a no longer needed
+        trace_at(q, tr, 7);
         wait_epilogue();       // Er: rh in P | Q
+        trace_at(q, tr, 8);
         for (int kb = 0; kb < 4; ++kb) kblock(dY, tP + kb * 32, tQ + kb * 32, false);  // C2
         umma_commit(acc_bar);
+        trace_at(q, tr, 9);
         umma_commit(pq_free);  // the next tile's gather-state k-blocks may stream into P | Q
       }
     }
@@ -365,8 +381,6 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
     const uint32_t tX = tmem_base + lane_base + COL_X, tY = tmem_base + lane_base + COL_Y;
     const uint32_t tP = tmem_base + lane_base + COL_P, tQ = tmem_base + lane_base + COL_Q;
     float *zrow = zrows + row_in_tile * ZLD;
-    const float4 g4 = reinterpret_cast<const float4 *>(s_gamma)[lane];
-    const float4 b4 = reinterpret_cast<const float4 *>(s_beta)[lane];
     uint32_t pacc = 0;
     auto wait_acc = [&]() {
       mbar_wait(acc_bar, pacc);
@@ -397,8 +411,10 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       const float *mrow = a.m + (valid ? row : (int64_t)a.row_begin) * a.ldm;
       const bool iso = valid && a.row_ptr && a.row_ptr[row] == a.row_ptr[row + 1];
 
+      const bool tr = (q.debug & 16) && tile == 2 * (int)gridDim.x && warp == 6 && lane == 0;
       // ---- E1: a = acc + bf  ->  P | Q
       wait_acc();
+      trace_at(q, tr, 16);
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
         float v[32];
@@ -409,9 +425,11 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       }
       tmem_st_wait();
       signal(epi_bar);
+      trace_at(q, tr, 17);
 
       // ---- Ez: z = sigmoid(acc + b_z)  ->  private shared row
       wait_acc();
+      trace_at(q, tr, 18);
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
         float v[32];
@@ -433,9 +451,11 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         }
       }
       signal(epi_bar);
+      trace_at(q, tr, 19);
 
       // ---- Er: rh = sigmoid(acc + b_r) * m  ->  P | Q   (a is dead: C1 has completed)
       wait_acc();
+      trace_at(q, tr, 20);
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
         float v[32];
@@ -454,9 +474,11 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       }
       tmem_st_wait();
       signal(epi_bar);
+      trace_at(q, tr, 21);
 
       // ---- E3: d = ((1 - z) m + z tanh(acc + b_h)) * keep, LayerNorm, store
       wait_acc();
+      trace_at(q, tr, 22);
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
         float v[32];
@@ -484,34 +506,61 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         }
       }
       signal(ring_free);  // Y has been read: the producers may stream the next tile's message rows into it
+      trace_at(q, tr, 23);
+      // LayerNorm.  Every thread normalises its own row in place; the sums follow the association of
+      // layernorm_fast_kernel<1> (rowops.cu) -- lane partials (x0 + x1) + (x2 + x3), then the xor-butterfly
+      // tree 16, 8, 4, 2, 1 -- so the rows this kernel writes carry the bits that kernel would give them
+      // (sparse levels mix the two), without a shuffle chain per row.
+      {
+        float p[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 x = *reinterpret_cast<const float4 *>(zrow + 4 * j);
+          p[j] = (x.x + x.y) + (x.z + x.w);
+        }
+#pragma unroll
+        for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+          for (int j = 0; j < w; ++j) p[j] = p[j] + p[j + w];
+        const float mean = p[0] * (1.0f / HF);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float4 x = *reinterpret_cast<const float4 *>(zrow + 4 * j);
+          x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+          p[j] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, 0.f))));
+        }
+#pragma unroll
+        for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+          for (int j = 0; j < w; ++j) p[j] = p[j] + p[j + w];
+        const float denom = sqrtf(p[0] * (1.0f / HF) + a.eps);
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          float4 x = *reinterpret_cast<const float4 *>(zrow + 4 * j);
+          const float4 g = *reinterpret_cast<const float4 *>(s_gamma + 4 * j);
+          const float4 b = *reinterpret_cast<const float4 *>(s_beta + 4 * j);
+          x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+          float4 o4;
+          o4.x = g.x * (x.x / denom) + b.x;
+          o4.y = g.y * (x.y / denom) + b.y;
+          o4.z = g.z * (x.z / denom) + b.z;
+          o4.w = g.w * (x.w / denom) + b.w;
+          *reinterpret_cast<float4 *>(zrow + 4 * j) = o4;
+        }
+      }
       const uint64_t dst_row = valid ? (a.scatter ? (uint64_t)a.scatter[row] : (uint64_t)row) : 0;
-      __syncwarp();  // the slab's d rows are visible to the whole warp
-      // LayerNorm, one row of the slab per warp instruction: lane l holds floats [4l, 4l + 4) of the row,
-      // the row is read from shared memory and written to global memory as 512 contiguous bytes.  Same
-      // arithmetic, in the same order, as layernorm_fast_kernel<1> (rowops.cu), so the rows this kernel
-      // normalises carry the bits that kernel would give them (sparse levels mix the two).
+      __syncwarp();  // the slab's rows are visible to the whole warp
+      // copy-out: one warp instruction moves one row of the slab (512 contiguous bytes)
       const float *slab = zrows + (quad * 32) * ZLD;
       const int64_t rows_left = a.rows - ((int64_t)tile * BLOCK_M + quad * 32);
       const int nrows = rows_left > 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
+#pragma unroll 4
       for (int r = 0; r < nrows; ++r) {
         const uint64_t dr = __shfl_sync(0xffffffffu, dst_row, r);
-        float4 x = *reinterpret_cast<const float4 *>(slab + r * ZLD + 4 * lane);
-        float sum = (x.x + x.y) + (x.z + x.w);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * (1.0f / HF);
-        x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
-        float var = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, 0.f))));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-        const float denom = sqrtf(var * (1.0f / HF) + a.eps);
-        float4 o4;
-        o4.x = g4.x * (x.x / denom) + b4.x;
-        o4.y = g4.y * (x.y / denom) + b4.y;
-        o4.z = g4.z * (x.z / denom) + b4.z;
-        o4.w = g4.w * (x.w / denom) + b4.w;
-        *reinterpret_cast<float4 *>(a.out + dr * (uint64_t)HF + 4 * lane) = o4;
+        const float4 x = *reinterpret_cast<const float4 *>(slab + r * ZLD + 4 * lane);
+        *reinterpret_cast<float4 *>(a.out + dr * (uint64_t)HF + 4 * lane) = x;
       }
+      trace_at(q, tr, 24);
       __syncwarp();  // before the next tile's Ez overwrites the slab
     }
   }
@@ -571,9 +620,25 @@ cudaError_t launch_upd_fused(const FusedUpdArgs &a, const TcWeights &w, bool sin
   q.num_tiles = (int)tiles;
   const int grid = (int)(tiles < sm_count ? tiles : sm_count);
   if (launches) ++*launches;
+  q.trace = nullptr;
+  if (q.debug & 16) {
+    static unsigned long long *buf = nullptr;
+    if (!buf && cudaMalloc(&buf, 32 * sizeof(unsigned long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+    cudaMemsetAsync(buf, 0, 32 * sizeof(unsigned long long), s);
+    q.trace = buf;
+  }
   upd_fused_kernel<<<grid, NUM_THREADS, kFusedSmem, s>>>(maps->hi3[TC_W_F], maps->lo3[TC_W_F],
                                                          maps->hi3[TC_W_ZR], maps->lo3[TC_W_ZR],
                                                          maps->hi3[TC_W_H], maps->lo3[TC_W_H], q);
+  if (q.debug & 16) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, q.trace, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "upd_fused trace (cycles from S1 start; MMA thread 0-9, epilogue 16-24):");
+    for (int i = 0; i < 32; ++i)
+      if (h[i]) fprintf(stderr, " [%d]=%lld", i, (long long)(h[i] - h[0]));
+    fprintf(stderr, "\n");
+  }
   return cudaGetLastError();
 }
 
