@@ -168,7 +168,8 @@ def kagg_roofline(H, heads, R, E, n, agg_ms, peak, peak_src, stage):
             "stage_ms": {"project": float(stage[0]), "aggregate": float(stage[1]), "update": float(stage[2])}}
 
 
-def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src, msg_only_rows=0.0):
+def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_src, msg_only_rows=0.0,
+                  update_launches=5):
     """The six projection GEMMs against min(tensor roof, HBM roof x intensity).  USEFUL FLOPs per node
     = 2 (D H + 11 H^2) (the reference's 12 Linears); the FP32-parity path issues `passes` TF32 MMAs per product and,
     in the single-row formulation, folded matrices (issued_flops_per_node).  `msg_only_rows`: rows without
@@ -187,7 +188,10 @@ def gemm_roofline(D, H, heads, R, n, gemm_ms, passes, hbm_peak, tf32_peak, tf32_
     intensity = issued_total / bytes_total  # MMA FLOPs the pipe must issue per HBM byte
     hbm_bound_tflops = hbm_peak * 1e9 * intensity / 1e12
     bound = min(tf32_peak, hbm_bound_tflops)
-    return {"kernels": "gemm_tc_kernel / gemm_tc_ts_kernel (K-proj + K-upd, 6 GEMMs + LayerNorm)",
+    kernels = ("gemm_tc_ts_kernel (K-proj, 2 GEMMs) + upd_fused_kernel (K-upd: out-proj, w_agg, GRU, dropout scale and "
+               "LayerNorm in one tcgen05 kernel)" if update_launches == 1 else
+               "gemm_tc_kernel / gemm_tc_ts_kernel (K-proj + K-upd, 6 GEMMs + LayerNorm)")
+    return {"kernels": kernels, "update_launches_per_block": update_launches,
             "bound": "tensor" if tf32_peak <= hbm_bound_tflops else "hbm", "unit": "TFLOP/s",
             "achieved": issued, "achieved_useful": useful, "peak": bound, "frac": issued / bound,
             "frac_useful": useful / bound, "tensor_peak": tf32_peak, "hbm_bound_tflops": hbm_bound_tflops,
@@ -411,7 +415,8 @@ def secondary_config3(h, a, hbm_peak, peak_src, tf32_peak, tf32_src):
            "roofline": roof,
            "rows_with_neighbours_per_level": active,
            "roofline_projections": gemm_roofline(d, d, heads, R, full, float(stage[0] + stage[2]), passes, hbm_peak,
-                                                 tf32_peak, tf32_src, msg_only_rows=msg_only),
+                                                 tf32_peak, tf32_src, msg_only_rows=msg_only,
+                                                 update_launches=layers[-1].update_launches),
            "hbm_used_gb": h.mem_used_gb(), "output_finite_sampled": finite}
     for o in layers:
         o.close()
@@ -486,7 +491,8 @@ def secondary_partitioned(h, a, hbm_peak, peak_src, tf32_peak, tf32_src, n, d, h
                "warmup": warmup, "edges_per_sec": E_total / (ms * 1e-3), "plan_build_s_rank0": round(plan_s, 3),
                "roofline": kagg_roofline(d, heads, R, float(E), float(n), float(stage[1]), hbm_peak, peak_src, stage),
                "roofline_projections": gemm_roofline(d, d, heads, R, float(n), float(stage[0] + stage[2]), passes,
-                                                     hbm_peak, tf32_peak, tf32_src),
+                                                     hbm_peak, tf32_peak, tf32_src,
+                                                     update_launches=layer.update_launches),
                "halo": halo_block(part, dist_, stats, "overlapped multi-pass"), "check": check,
                "overlap_mode": None if ms_other is None else {
                    "ms_per_step": ms_other, "value": n * world / (ms_other * 1e-3), "gather_passes": stats_other["passes"],
@@ -609,7 +615,8 @@ def main():
                 "edges_per_sec": E_total / (ms_per_step * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                 "roofline_projections": gemm_roofline(a.dim, H, a.heads, R, float(n), float(stage[0] + stage[2]), passes,
-                                                      hbm_peak, tf32_peak, tf32_src),
+                                                      hbm_peak, tf32_peak, tf32_src,
+                                                      update_launches=layer.update_launches),
             }
             if world > 1:
                 line["halo"] = halo_block(part, dist_, stats, "overlapped multi-pass")

@@ -122,6 +122,11 @@ int32_t ruvgnn_layer_dims(const ruvgnn_layer *layer, uint32_t *input_dim, uint32
                           uint32_t *heads, float *dropout);
 int32_t ruvgnn_layer_set_mode(ruvgnn_layer *layer, uint32_t mode);
 uint32_t ruvgnn_layer_mode(const ruvgnn_layer *layer);
+/* Kernel launches of the update phase (out-proj + combine + w_agg, GRU, dropout scale, LayerNorm:
+ * layer.rs:156-159,407-417) per row block in the layer's current mode: 1 when the whole chain runs as the
+ * fused kernel (hidden_dim == 128, tensor-core modes; every embedding row is then written once and no
+ * intermediate touches HBM), 5 otherwise (four GEMMs + LayerNorm). */
+uint32_t ruvgnn_layer_update_launches(const ruvgnn_layer *layer);
 void ruvgnn_layer_destroy(ruvgnn_layer *layer);
 
 /* ---- graph: HNSW neighbour lists -> device CSR ------------------------- */

@@ -70,6 +70,7 @@ SYMBOLS = {
     "ruvgnn_layer_project": (C.c_int32, [_vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_project_rows": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64]),
     "ruvgnn_layer_halo_width": (C.c_uint32, [_vp]),
+    "ruvgnn_layer_update_launches": (C.c_uint32, [_vp]),
     "ruvgnn_halo_pack": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "ruvgnn_layer_messages": (C.c_int32, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "ruvgnn_layer_expand_halo": (C.c_int32, [_vp, _vp, _vp, C.c_uint64, _vp]),

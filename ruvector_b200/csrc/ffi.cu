@@ -1026,6 +1026,11 @@ uint32_t ruvgnn_layer_mode(const ruvgnn_layer *layer) {
   return layer ? layer->mode : RUVGNN_MODE_FP32_SIMT;
 }
 
+uint32_t ruvgnn_layer_update_launches(const ruvgnn_layer *layer) {
+  if (!layer) return 0;
+  return (layer->fused_upd && layer->mode != RUVGNN_MODE_FP32_SIMT) ? 1u : 5u;
+}
+
 void ruvgnn_layer_destroy(ruvgnn_layer *L) {
   if (!L) return;
   DeviceGuard dg(L->device);

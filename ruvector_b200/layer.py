@@ -301,6 +301,12 @@ class RuvectorLayer:
         allows it, else ``MODE_FP32_SIMT``)."""
         return int(_lib.load().ruvgnn_layer_mode(self._device_layer()))
 
+    @property
+    def update_launches(self) -> int:
+        """Kernel launches of the update phase per row block: 1 = the fused kernel (hidden_dim 128,
+        tensor-core modes), 5 = four GEMMs + LayerNorm."""
+        return int(_lib.load().ruvgnn_layer_update_launches(self._device_layer()))
+
     def set_mode(self, mode: int):
         self._mode = mode
         if self._handle is not None:

@@ -52,6 +52,7 @@ SHAPES = [
 def test_fused_update_matches_oracle_and_unfused(oracle, ctx, n, d, heads, m):
     fused = make_layer(d, heads, n + 1, ctx, True)
     plain = make_layer(d, heads, n + 1, ctx, False)
+    assert fused.update_launches == 1 and plain.update_launches == 5
     x = synth.make_features(n, d, seed=n + 2)
     g = synth.hnsw_like_graph(n, m, seed=n + 3, iso_frac=0.05)
     dg = g.to_device(ctx)
@@ -123,6 +124,7 @@ def test_fused_update_simt_mode_is_untouched(oracle, ctx):
     plain = make_layer(d, heads, 21, ctx, False)
     fused.set_mode(rv.MODE_FP32_SIMT)
     plain.set_mode(rv.MODE_FP32_SIMT)
+    assert fused.update_launches == 5
     x = synth.make_features(n, d, seed=22)
     g = synth.hnsw_like_graph(n, 8, seed=23)
     dg = g.to_device(ctx)
