@@ -593,6 +593,10 @@ cudaError_t launch_upd_fused(const FusedUpdArgs &a, const TcWeights &w, bool sin
                              cudaStream_t s, uint64_t *launches) {
   if (a.rows <= 0) return cudaSuccess;
   if (!upd_fused_supported(w, HF) || (uint32_t)a.K1 != w.cols[TC_W_F]) return cudaErrorInvalidValue;
+  // the row-per-thread 256-bit loads and the 128-bit row stores need 32- / 16-byte aligned rows
+  if (((reinterpret_cast<uintptr_t>(a.A1) | reinterpret_cast<uintptr_t>(a.m)) & 31) != 0 ||
+      (reinterpret_cast<uintptr_t>(a.out) & 15) != 0 || (a.lda1 & 7) != 0 || (a.ldm & 7) != 0)
+    return cudaErrorMisalignedAddress;
   const TcMaps *maps = static_cast<const TcMaps *>(w.tmaps);
   static bool configured_dev[64] = {};
   int dev = 0;
