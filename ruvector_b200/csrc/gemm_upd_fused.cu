@@ -30,6 +30,8 @@
 // producers (one tile row per thread), warps 6-9 epilogue.  Per tile the MMA warp runs
 //   S1 (K1/32 k-blocks, A streamed) | E1 | Z (a resident, m streamed) | Ez | R | C1 (a resident)
 //   | Er | C2 (rh resident) | E3
+// (the gate math of Ez runs under R, that of Er under C1: only the accumulator read-out and the hi | lo
+// split of an operand stand between two dependent GEMMs)
 // with the E phases on the epilogue warps.  Weight k-blocks keep streaming through the phases.  In Z
 // and R the resident and the streamed k-blocks alternate (a0 m0 a1 m1 ..), so a ring slot has two
 // k-blocks of MMA time to be refilled.
@@ -108,7 +110,8 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
   uint64_t *ring_free = acc_bar + 2;       // epilogue -> A producers: Y holds no accumulator any more
   uint64_t *drain_bar = acc_bar + 3;       // MMA -> MMA: the MMAs that read the Y ring as A have completed
   uint64_t *pq_free = acc_bar + 4;         // MMA -> A producers: the last MMAs reading rh from P | Q have completed
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_bar + 5);
+  uint64_t *r_done = acc_bar + 5;          // MMA -> epilogue: the R GEMM is complete (C1 may still be running)
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_bar + 6);
 
   for (int i = threadIdx.x; i < HF; i += NUM_THREADS) {
     vecs[i] = a.bf[i];
@@ -142,6 +145,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
     mbar_init(ring_free, 4);
     mbar_init(drain_bar, 1);
     mbar_init(pq_free, 1);
+    mbar_init(r_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -258,7 +262,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
             kblock(dX, tP + kb * 32, tQ + kb * 32, kb == 0);
             m_kblock(dX);
           }
-          if (half == 0) umma_commit(acc_bar);
+          umma_commit(half == 0 ? acc_bar : r_done);
           trace_at(q, tr, 3 + 2 * half);
         }
         // C1: Y = a Wh[:, 0:128]^T.  Y was the message-row ring until here; the producers hold until
@@ -381,7 +385,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
     const uint32_t tX = tmem_base + lane_base + COL_X, tY = tmem_base + lane_base + COL_Y;
     const uint32_t tP = tmem_base + lane_base + COL_P, tQ = tmem_base + lane_base + COL_Q;
     float *zrow = zrows + row_in_tile * ZLD;
-    uint32_t pacc = 0;
+    uint32_t pacc = 0, pr = 0;
     auto wait_acc = [&]() {
       mbar_wait(acc_bar, pacc);
       pacc ^= 1;
@@ -427,49 +431,59 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       signal(epi_bar);
       trace_at(q, tr, 17);
 
-      // ---- Ez: z = sigmoid(acc + b_z)  ->  private shared row
+      // ---- Ez: z = sigmoid(acc + b_z)  ->  private shared row.  The accumulator is copied out first and X handed
+      // back at once, so the R GEMM runs under the sigmoids (they work on the copy, in place).
       wait_acc();
       trace_at(q, tr, 18);
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
         float v[32];
         tmem_ld32(tX + (uint32_t)c, v);
-        if (q.debug & 8) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4 *>(zrow + c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 z;
-          z.x = sigmoid_ref(v[4 * j + 0] + s_bz[c + 4 * j + 0]);
-          z.y = sigmoid_ref(v[4 * j + 1] + s_bz[c + 4 * j + 1]);
-          z.z = sigmoid_ref(v[4 * j + 2] + s_bz[c + 4 * j + 2]);
-          z.w = sigmoid_ref(v[4 * j + 3] + s_bz[c + 4 * j + 3]);
-          *reinterpret_cast<float4 *>(zrow + c + 4 * j) = z;
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4 *>(zrow + c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
       signal(epi_bar);
       trace_at(q, tr, 19);
+      if (!(q.debug & 8)) {
+#pragma unroll 4
+        for (int j = 0; j < HF / 4; ++j) {
+          float4 z = *reinterpret_cast<const float4 *>(zrow + 4 * j);
+          z.x = sigmoid_ref(z.x + s_bz[4 * j + 0]);
+          z.y = sigmoid_ref(z.y + s_bz[4 * j + 1]);
+          z.z = sigmoid_ref(z.z + s_bz[4 * j + 2]);
+          z.w = sigmoid_ref(z.w + s_bz[4 * j + 3]);
+          *reinterpret_cast<float4 *>(zrow + 4 * j) = z;
+        }
+      }
 
-      // ---- Er: rh = sigmoid(acc + b_r) * m  ->  P | Q   (a is dead: C1 has completed)
-      wait_acc();
+      // ---- Er: rh = sigmoid(acc + b_r) * m  ->  P | Q.  r is complete as soon as the R GEMM is (r_done), but
+      // P | Q still hold a until C1 has read it: the gate math runs under C1 and parks rh in X (the thread's own
+      // TMEM row, free until the next tile); once C1 has completed only the split into P | Q remains.
+      mbar_wait(r_done, pr);
+      pr ^= 1;
+      tc_fence_after();
       trace_at(q, tr, 20);
+      if (!(q.debug & 8)) {
+#pragma unroll 1
+        for (int c = 0; c < HF; c += 32) {
+          float4 mm[8];
+          ld_row32(mrow + c, mm);
+          float v[32];
+          tmem_ld32(tX + (uint32_t)c, v);
+          const float *mf = reinterpret_cast<const float *>(mm);
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(sigmoid_ref(v[j] + s_br[c + j]) * mf[j]);
+          tmem_st32(tX + (uint32_t)c, r);
+        }
+        tmem_st_wait();
+      }
+      wait_acc();  // C1 complete: a is dead
 #pragma unroll 1
       for (int c = 0; c < HF; c += 32) {
         float v[32];
-        if (q.debug & 8) {
-          tmem_ld32(tX + (uint32_t)c, v);
-          store_operand(c, v);
-          continue;
-        }
-        float4 mm[8];
-        ld_row32(mrow + c, mm);
         tmem_ld32(tX + (uint32_t)c, v);
-        const float *mf = reinterpret_cast<const float *>(mm);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = sigmoid_ref(v[j] + s_br[c + j]) * mf[j];
         store_operand(c, v);
       }
       tmem_st_wait();
