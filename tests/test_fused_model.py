@@ -137,3 +137,23 @@ def test_ring_bookkeeping_of_one_tile(k1):
     s1_slots = [cols["P"] + 64 * s for s in range(4)]
     m_slots = [cols["Y"] + 64 * s for s in range(2)]
     assert s1_slots[-1] + 64 == 512 and m_slots[-1] + 64 == cols["P"]
+
+
+def test_cycle_model_reproduces_the_recorded_timeline():
+    """scripts/fused_upd_model.py (per-MMA issue cost by commit density + exposed epilogues) against the clock64
+    timeline recorded on a B200 (profiles/r02t_upd_fused_timeline.txt, slot 9 = end of the tile's last GEMM)."""
+    import importlib.util
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("fused_upd_model", root / "scripts" / "fused_upd_model.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    trace = dict((int(k), int(v)) for k, v in re.findall(r"\[(\d+)\]=(\d+)", (root / "profiles" / "r02t_upd_fused_timeline.txt").read_text()))
+    measured = trace[9]
+    assert abs(mod.tile_cycles(640) - measured) / measured < 0.05
+    # the phases the model is built from, as measured: S1, Z, R, C1, C2 issue spans
+    assert abs((trace[1] - trace[0]) - 20 * 12 * 138.0) / (trace[1] - trace[0]) < 0.05
+    assert abs((trace[3] - trace[2]) - 8 * 12 * 103.0) / (trace[3] - trace[2]) < 0.05
+    assert abs((trace[9] - trace[8]) - 4 * 12 * 90.0) / (trace[9] - trace[8]) < 0.05
