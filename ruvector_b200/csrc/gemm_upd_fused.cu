@@ -64,6 +64,7 @@ struct FusedParams {
               // 8 = no activation math / message loads in the epilogues.  Results are garbage.
               // 16 = phase timeline of CTA 0's third tile (clock64) into `trace`, printed by the launcher.
   unsigned long long *trace;
+  int gate;  // RUVGNN_FUSED_GATE: the MMA warp waits for the previous tile's ring_free before it completes stage 1
 };
 
 __device__ __forceinline__ void trace_at(const FusedParams &q, bool on, int slot) {
@@ -199,6 +200,7 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
       const uint32_t tP = tmem_base + COL_P, tQ = tmem_base + COL_Q;
       int ss = 0, sm = 0, sb = 0;
       uint32_t ps = 0, pm = 0, pb = 0, pe = 0, pd = 0;
+      uint32_t tiles_issued = 0;
       // one weight k-block against one A k-block (hi at ah, remainder at al)
       auto kblock = [&](uint32_t d, uint32_t ah, uint32_t al, bool first_kb) {
         mbar_wait(&full_b[sb], pb);
@@ -253,6 +255,15 @@ upd_fused_kernel(const __grid_constant__ CUtensorMap mf_hi, const __grid_constan
         const bool tr = (q.debug & 16) && tile == 2 * (int)gridDim.x;
         trace_at(q, tr, 0);
         for (int kb = 0; kb < NK1; ++kb) s_kblock(dX, kb == 0);  // S1: X = [S | agg] Wf^T
+        // Stage 1 of this tile ran under the previous tile's last epilogue.  acc_bar is a two-phase (parity) barrier:
+        // its next completion must not happen before every epilogue warp has OBSERVED the previous one (C2 of the
+        // previous tile), or a warp that stalled for a whole stage 1 (~19 us) would wait on the wrong phase
+        // (tests/test_fused_protocol.py finds that schedule).  ring_free of the previous tile is arrived by all four
+        // epilogue warps after they passed that wait.  Opt-in (RUVGNN_FUSED_GATE=1) this round: written after the
+        // round's GPU budget was spent, so the default instruction stream is the validated one; a spinning warp
+        // does not stall that long on this hardware, and every mbarrier wait traps after 4 s rather than hanging.
+        if (q.gate && tiles_issued > 0) mbar_wait(ring_free, (tiles_issued - 1) & 1);
+        ++tiles_issued;
         umma_commit(acc_bar);
         trace_at(q, tr, 1);
         for (int half = 0; half < 2; ++half) {  // Z, then R: X = [a | m] Wzr[half]^T
@@ -633,6 +644,12 @@ cudaError_t launch_upd_fused(const FusedUpdArgs &a, const TcWeights &w, bool sin
       dbg = e ? atoi(e) : 0;
     }
     q.debug = dbg;
+    static int gate = -1;
+    if (gate < 0) {
+      const char *e = getenv("RUVGNN_FUSED_GATE");
+      gate = e ? atoi(e) : 0;
+    }
+    q.gate = gate;
   }
   const int64_t tiles = (a.rows + BLOCK_M - 1) / BLOCK_M;
   q.num_tiles = (int)tiles;
